@@ -1,0 +1,148 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run only in the build container (needs /root/reference):  python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors for the fusion path, so
+parity is pinned by executing the reference itself (oracle/ref_harness.py: import shims + its CUDA
+kernel string compiled verbatim for the host) on deterministic synthetic inputs
+(boxfusion_b200/synthetic.py) and freezing inputs and outputs here.  Environment of record is
+written to golden_meta.json (numpy / scipy / torch versions matter: SURVEY F8).
+"""
+import io
+import contextlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh                      # noqa: E402
+from boxfusion_b200.synthetic import (SyntheticScene, make_cfg, map_and_detections,     # noqa: E402
+                                      refine_problem)
+from boxfusion_b200.driver import FusionSession           # noqa: E402
+
+REF_PST = os.path.join(rh.REFERENCE_ROOT, "data", "pst_1024_0.tiff")
+
+SEQUENCES = {
+    "seq_ca1m": dict(n_objects=40, seed=1, max_det=20, shape="ca1m", tilt_noise=0.0, frames=12),
+    "seq_scannet_tilt": dict(n_objects=40, seed=2, max_det=20, shape="scannet", tilt_noise=0.02, frames=10),
+}
+
+
+def gen_pst(ref):
+    import cv2
+    pst = np.ascontiguousarray(cv2.imread(REF_PST, -1))
+    assert pst.shape == (1024, 6) and pst.dtype == np.float32
+    np.save(os.path.join(HERE, "pst_1024_0.npy"), pst)
+    return pst
+
+
+def gen_sequence(ref, name, spec):
+    spec = dict(spec)
+    frames = spec.pop("frames")
+    scene = SyntheticScene(**spec)
+    cfg = make_cfg(spec["shape"], pst_path=REF_PST, pst_size=1024)
+    sess = FusionSession(ref, cfg)
+    out = {"n_frames": np.array(frames)}
+    for k in range(frames):
+        kf = scene.keyframe(k)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ins, pose_np = sess.make_pred_instances(kf)       # demo.py:216-221 with the reference's own ops
+        out[f"k{k}_tensor_w"] = ins.pred_boxes_3d.tensor.numpy().copy()
+        out[f"k{k}_R_w"] = ins.pred_boxes_3d.R.numpy().copy()
+        out[f"k{k}_projected"] = ins.projected_boxes.numpy().copy()
+        sess.step(kf, ins, pose_np)
+        for key, val in sess.snapshot().items():
+            out[f"k{k}_snap_{key}"] = val
+        out[f"k{k}_mask"] = np.asarray(sess.last_mask if sess.last_mask is not None else [], dtype=np.int64)
+        out[f"k{k}_success"] = np.asarray(sess.last_success if sess.last_success is not None else [], dtype=np.int64)
+        sess.last_mask = sess.last_success = None
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "map", len(sess.all_pred_box), "fused", len(sess.box_manager.already_fusion))
+
+
+def gen_iou_pairs(ref):
+    (mt, mR, ms), (dt, dR, ds) = map_and_detections(60, 24, seed=11, tilt_noise=0.01)
+    t = np.concatenate([mt, dt]); R = np.concatenate([mR, dR])
+    corners = ref.GeneralInstance3DBoxes(torch.from_numpy(t), torch.from_numpy(R)).corners.numpy()
+    n = t.shape[0]
+    ia, ib = np.triu_indices(n, 1)
+    iou = np.array([ref.Instances3D.obb_iou(corners[a], corners[b]) for a, b in zip(ia, ib)], dtype=np.float64)
+    # 240 deliberately overlapping pairs (a box and a noisy re-observation) so the sampled branch
+    # (instances.py:585-608) is well covered
+    from boxfusion_b200.synthetic import random_boxes, box_rotation
+    rs = np.random.RandomState(5)
+    bt, bR = random_boxes(240, 21, tilt_noise=0.01)
+    yaw = np.arctan2(bR[:, 1, 0], bR[:, 0, 0]) + rs.normal(0, 0.15, 240)
+    ot = np.concatenate([bt[:, :3] + rs.normal(0, 0.12, (240, 3)), bt[:, 3:] * np.exp(rs.normal(0, 0.2, (240, 3)))], 1)
+    oR = box_rotation(yaw, rs.normal(0, 0.01, 240), rs.normal(0, 0.01, 240)).astype(np.float32)
+    ca = ref.GeneralInstance3DBoxes(torch.from_numpy(bt), torch.from_numpy(bR)).corners.numpy()
+    cb = ref.GeneralInstance3DBoxes(torch.from_numpy(ot.astype(np.float32)), torch.from_numpy(oR)).corners.numpy()
+    iou2 = np.array([ref.Instances3D.obb_iou(ca[i], cb[i]) for i in range(240)], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "iou_pairs.npz"), tensor=t, R=R, corners=corners,
+                        ia=ia.astype(np.int32), ib=ib.astype(np.int32), iou=iou,
+                        ov_a=ca, ov_b=cb, ov_iou=iou2)
+    print("overlap pairs", len(iou2), "nonzero", int((iou2 > 0).sum()))
+    print("iou_pairs", len(iou), "nonzero", int((iou > 0).sum()), "over thr", int((iou > 0.1).sum()))
+
+
+def gen_refine(ref, pst):
+    out = {}
+    cfg = make_cfg("ca1m", pst_path=REF_PST, pst_size=1024)
+    for V in (3, 5, 8):
+        prob = refine_problem(6, V, seed=100 + V)
+        W, H = prob["size"]
+        bf = ref.BoxFusion(cfg)
+        bf.update_intrinsics((W, H), prob["K"])
+        B = prob["tensor"].shape[0]
+        per = ref.Instances3D((H, W))
+        per.pred_boxes_3d = ref.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"].reshape(-1, 6)),
+                                                       torch.from_numpy(prob["R"].reshape(-1, 3, 3)))
+        per.cam_pose = torch.from_numpy(prob["poses"].reshape(-1, 4, 4))
+        per.scores = torch.from_numpy(prob["scores"].reshape(-1))
+        per.pred_boxes = torch.zeros(B * V, 4)
+        per.project_3d_boxes(prob["K"], H=H, W=W)
+        proj = per.projected_boxes.numpy().reshape(B, V, 8, 2)
+        search = np.array([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], np.float32)
+        fit = np.stack([bf.evaluate_iou(prob["tensor"][b, 0].astype(np.float64), proj[b], prob["R"][b, 0],
+                                        prob["scores"][b], prob["poses"][b], search, V) for b in range(B)])
+        allp = ref.Instances3D((H, W))
+        allp.pred_boxes_3d = ref.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][:, 0].copy()),
+                                                        torch.from_numpy(prob["R"][:, 0].copy()))
+        bm = ref.BoxManager(cfg)
+        bm.fusion_list = [list(range(b * V, (b + 1) * V)) for b in range(B)]
+        bm.fusion_flag = [0] * B
+        with contextlib.redirect_stdout(io.StringIO()):
+            bf.boxfusion(allp, per, bm)
+        for k in ("tensor", "R", "scores", "poses", "K"):
+            out[f"v{V}_{k}"] = prob[k]
+        out[f"v{V}_size"] = np.array(prob["size"])
+        out[f"v{V}_projected"] = proj
+        out[f"v{V}_fitness0"] = fit
+        out[f"v{V}_fused"] = allp.pred_boxes_3d.tensor.numpy().copy()
+        out[f"v{V}_flag"] = np.array(bm.fusion_flag)
+        print("refine V", V, "fused", sum(bm.fusion_flag))
+    np.savez_compressed(os.path.join(HERE, "refine_cases.npz"), **out)
+
+
+def main():
+    ref = rh.load_reference()
+    pst = gen_pst(ref)
+    for name, spec in SEQUENCES.items():
+        gen_sequence(ref, name, spec)
+    gen_iou_pairs(ref)
+    gen_refine(ref, pst)
+    import scipy
+    meta = {"numpy": np.__version__, "scipy": scipy.__version__, "torch": torch.__version__,
+            "reference": "pliam1105/BoxFusion @ /root/reference", "sequences": SEQUENCES,
+            "note": "reference kernel string compiled for the host with g++ -O2 -ffp-contract=off"}
+    json.dump(meta, open(os.path.join(HERE, "golden_meta.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
