@@ -1,0 +1,123 @@
+"""ctypes binding of libboxfusion_sm100.so (include/boxfusion_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or no sm_100 device is
+present, importing callers get a RuntimeError the first time they touch the hot path.
+PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libboxfusion_sm100.so")
+
+BF_OK, BF_ERR_INVALID_ARG, BF_ERR_CUDA, BF_ERR_CAPACITY = 0, -1, -2, -3
+IOU_SAMPLED_REF, IOU_ANALYTIC = 0, 1
+_ERR = {-1: "BF_ERR_INVALID_ARG", -2: "BF_ERR_CUDA", -3: "BF_ERR_CAPACITY"}
+
+_vp, _i32, _f32, _f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
+
+
+class RefineCfg(ctypes.Structure):
+    """bf_refine_cfg (include/boxfusion_b200.h)."""
+    _fields_ = [("iters", ctypes.c_int32), ("pst_size", ctypes.c_int32),
+                ("center_init", _f32), ("shape_init", _f32), ("center_scale", _f32), ("shape_scale", _f32),
+                ("beta", _f64), ("img_h", _f32), ("img_w", _f32),
+                ("fx", _f32), ("cx", _f32), ("fy", _f32), ("cy", _f32),
+                ("max_hits", ctypes.c_int32), ("early_stop", ctypes.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/boxfusion_b200.h
+PROTOTYPES = {
+    "bf_version": (_i32, []),
+    "bf_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
+    "bf_destroy": (None, [_vp]),
+    "bf_last_error": (ctypes.c_char_p, [_vp]),
+    "bf_fusion_cap": (_i32, []),
+    "bf_box_corners": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bf_transform2world": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "bf_project_boxes": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "bf_iou3d_matrix": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "bf_nms3d": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f32, _f32, _f32, _i32,
+                        _vp, _vp, _vp, _vp]),
+    "bf_corr2d": (_i32, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "bf_pose_disparity": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bf_refine": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, ctypes.POINTER(RefineCfg),
+                         _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
+}
+
+_LIB: Optional[ctypes.CDLL] = None
+_HANDLES: Dict[int, "Handle"] = {}
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree library and bind every exported symbol (no GPU needed for this step)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m boxfusion_b200.build` "
+                "(boxfusion_b200 has no CPU or PyTorch fallback for the fusion hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so does not export the symbol
+            fn.restype, fn.argtypes = res, args
+        _LIB = lib
+    return _LIB
+
+
+class Handle:
+    """One bf_handle per CUDA device."""
+
+    def __init__(self, device: int):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("boxfusion_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+        self.device = device
+        torch.cuda.init()
+        with torch.cuda.device(device):
+            torch.zeros(1, device=f"cuda:{device}")    # make sure the primary context exists
+            h = _vp()
+            rc = self.lib.bf_create(device, ctypes.byref(h))
+            if rc != BF_OK:
+                raise RuntimeError(f"bf_create({device}) failed: {_ERR.get(rc, rc)}: "
+                                   f"{self.lib.bf_last_error(None).decode()}")
+        self.h = h
+
+    def check(self, rc: int, what: str):
+        if rc != BF_OK:
+            raise RuntimeError(f"{what}: {_ERR.get(rc, rc)}: {self.lib.bf_last_error(self.h).decode()}")
+
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+
+def handle(device=None) -> Handle:
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    device = int(device)
+    if device not in _HANDLES:
+        _HANDLES[device] = Handle(device)
+    return _HANDLES[device]
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device pointer arguments must be contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def dev_tensor(x, dtype, device) -> torch.Tensor:
+    """Contiguous tensor of `dtype` on `device` (copies host data; no-op for matching CUDA tensors)."""
+    if not isinstance(x, torch.Tensor):
+        import numpy as np
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()

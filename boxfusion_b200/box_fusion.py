@@ -1,0 +1,182 @@
+"""`boxfusion.box_fusion.BoxFusion` for the B200 path (reference: boxfusion/box_fusion.py:27-724).
+
+The reference JIT-compiles a PyCUDA kernel and, per map box and per optimiser iteration, does 13
+blocking host<->device copies around a one-warp-per-block launch plus a Python reduction
+(box_fusion.py:432-452, 475-535).  Here `boxfusion()` gathers every fusable box of the keyframe and
+refines them all in ONE bf_refine launch (one CTA per box, all iterations on the device); the host
+only selects which boxes qualify (fusion_list length >= 3 and view set not fused before,
+box_fusion.py:634) and writes the fused rows back (:716-724).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _load_pst(path) -> np.ndarray:
+    """Particle-swarm template [P,6] float32 (box_fusion.py:31-32 reads a TIFF with cv2)."""
+    if isinstance(path, np.ndarray):
+        pst = path
+    elif str(path).endswith(".npy"):
+        pst = np.load(path)
+    else:
+        import cv2
+        pst = cv2.imread(str(path), -1)
+        if pst is None:
+            raise FileNotFoundError(f"cannot read particle template {path}")
+    pst = np.ascontiguousarray(pst, dtype=np.float32)
+    assert pst.ndim == 2 and pst.shape[1] == 6, "PST must be [P,6]"
+    return pst
+
+
+class BoxFusion(object):
+    def __init__(self, cfg) -> None:
+        self.cfg = cfg
+        self.PST_path = cfg["box_fusion"]["pst_path"]
+        self.PST = _load_pst(self.PST_path)
+        self.basedir = cfg["data"]["datadir"]
+        if "scannet" in str(self.basedir).lower() or cfg["dataset"] == "online" or "fx" in cfg["cam"]:
+            cam = cfg["cam"]
+            self.K = np.array([[cam["fx"], 0.0, cam["cx"], 0.0], [0.0, cam["fy"], cam["cy"], 0.0],
+                               [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
+            self.H, self.W = cam["H"], cam["W"]
+        else:                                    # CA-1M layout on disk (box_fusion.py:44-51)
+            k = np.loadtxt(os.path.join(self.basedir, "K_depth.txt")).reshape(3, 3)
+            self.K = np.array([[k[0, 0], 0.0, k[0, 2], 0.0], [0.0, k[1, 1], k[1, 2], 0.0],
+                               [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
+            self.H, self.W = cfg["cam"]["W"], cfg["cam"]["H"]
+        self.update_K_flag = False
+        bf = cfg["box_fusion"]
+        self.fusion_iters = bf["iters"]
+        self.pst_size = bf["pst_size"]
+        self.center_init_size = bf["random_opt"]["center_init_size"]
+        self.center_scaling_coefficient = bf["random_opt"]["center_scaling_coefficient"]
+        self.shape_init_size = bf["random_opt"]["shape_init_size"]
+        self.shape_scaling_coefficient = bf["random_opt"]["shape_scaling_coefficient"]
+        self.early_stop = True                   # reference behaviour; benches may force all iterations
+        self._pst_dev = {}
+        self.last_iters = None                   # per refined box: evaluate_iou calls the optimiser made
+        self.init_searchsize()
+
+    # ---- small state helpers (box_fusion.py:463-472) -----------------------------------------------
+    def update_intrinsics(self, size, K):
+        self.H = size[1]
+        self.W = size[0]
+        self.K[:3, :3] = np.asarray(K)
+
+    def init_searchsize(self):
+        self.search_size = np.zeros(6, dtype=np.float32)
+        self.previous_search_size = np.zeros(6, dtype=np.float32)
+        self.search_size[:3] = self.center_init_size
+        self.search_size[3:] = self.shape_init_size
+
+    def _pst_on(self, dev) -> torch.Tensor:
+        key = str(dev)
+        if key not in self._pst_dev:
+            self._pst_dev[key] = torch.from_numpy(self.PST).to(dev)
+        return self._pst_dev[key]
+
+    def _rcfg(self, beta=0.9, iters=None):
+        return ops.make_refine_cfg(self.cfg, self.K.reshape(-1), self.H, self.W, beta=beta,
+                                   early_stop=self.early_stop, iters=iters)
+
+    # ---- evaluate_iou (box_fusion.py:413-461) -------------------------------------------------------
+    def evaluate_iou(self, box_3d, corners_2d, box_rot, scores_box, camera_poses, search_size, num_of_boxes,
+                     verbose=False):
+        """fitness[P] of every particle of the template around `box_3d` (numpy float32, like the reference)."""
+        dev = ops._dev()
+        uv = np.asarray(corners_2d, dtype=np.float32).reshape(-1, 16)[:num_of_boxes]
+        poses = np.asarray(camera_poses, dtype=np.float32).reshape(-1, 16)[:num_of_boxes]
+        fit = ops.evaluate_iou(self._pst_on(dev), np.asarray(box_3d, dtype=np.float32).reshape(6),
+                               np.asarray(box_rot, dtype=np.float32).reshape(9), uv, poses,
+                               np.asarray(search_size, dtype=np.float32).reshape(6), self._rcfg())
+        return fit.cpu().numpy()
+
+    # ---- host mirrors of the optimiser's scalar steps, kept for API completeness; boxfusion() does not
+    #      call them (the same arithmetic runs inside bf_refine) ------------------------------------------
+    def cal_transform(self, search_value, search_size):
+        """box_fusion.py:475-535 (float32 sequential sums, first-200 rule)."""
+        sv = np.asarray(search_value, dtype=np.float32)
+        origin = sv[0]
+        hit = np.nonzero(sv[1:] < origin)[0][:200] + 1
+        mean_transform = np.zeros(6, dtype=np.float32)
+        if len(hit) == 0:
+            return False, origin, mean_transform
+        acc = np.zeros(8, dtype=np.float32)
+        for j in hit:
+            w = np.float32(origin - sv[j])
+            acc[:6] += self.PST[j] * w
+            acc[6] += w
+            acc[7] += sv[j] * w
+        mean_transform[:] = (acc[:6] / acc[6]) * np.asarray(search_size, dtype=np.float32)
+        return True, acc[7] / acc[6], mean_transform
+
+    def update_PST(self, iou, mean_transform, min_scale=1e-3, center_scale=0.5, shape_scale=0.5):
+        """box_fusion.py:537-562."""
+        s = np.abs(np.asarray(mean_transform, dtype=np.float32)) + np.float32(min_scale)
+        n2 = s[0] * s[0]
+        for k in range(1, 6):
+            n2 = n2 + s[k] * s[k]
+        nrm = np.sqrt(n2)
+        iou = np.float32(iou)
+        for k in range(3, 6):
+            self.search_size[k] = np.float32(shape_scale) * iou * (s[k] / nrm) + np.float32(min_scale)
+        for k in range(3):
+            self.search_size[k] = np.float32(center_scale) * iou * (s[k] / nrm) + np.float32(min_scale)
+
+    def init_opt_params(self, box_3d, per_boxes_3d_R, per_boxes_3d_scores, verbose=False):
+        """box_fusion.py:566-600."""
+        box_3d = np.asarray(box_3d)
+        best = int(np.argmax(per_boxes_3d_scores))
+        mean = np.zeros(6)
+        mean[:3] = np.mean(box_3d[:, :3], axis=0)
+        rank = np.argsort(np.argsort(box_3d[best, 3:]))
+        mean[3:6] = np.mean(np.sort(box_3d[:, 3:], axis=1)[:, list(rank)], axis=0)
+        return mean, per_boxes_3d_R[best]
+
+    # ---- the hot path (box_fusion.py:622-724) --------------------------------------------------------
+    def boxfusion(self, all_pred_box, per_frame_box, box_manager, beta=0.9, verbose=False):
+        N_box = len(all_pred_box)
+        fl = box_manager.fusion_list
+        todo = [i for i in range(N_box) if len(fl[i]) >= 3 and not box_manager.check_if_fusion(fl[i])]
+        self.last_iters = None
+        if not todo:
+            return
+        boxes = per_frame_box.get("pred_boxes_3d")
+        dev = ops._pick_device(boxes.tensor, all_pred_box.pred_boxes_3d.tensor)
+        lens = [len(fl[i]) for i in todo]
+        if max(lens) > ops.MAX_VIEWS:
+            raise RuntimeError(f"a fusion list has {max(lens)} views; bf_refine supports {ops.MAX_VIEWS}")
+        offsets = np.zeros(len(todo) + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum(lens)
+        index = np.fromiter((int(v) for i in todo for v in fl[i]), dtype=np.int32, count=int(offsets[-1]))
+        csr = torch.from_numpy(np.concatenate([offsets, index])).to(dev, non_blocking=True)
+        out, upd, its, _, status = ops.refine(
+            self._pst_on(dev), boxes.tensor, boxes.R, per_frame_box.scores, per_frame_box.projected_boxes,
+            per_frame_box.cam_pose, csr[: len(todo) + 1], csr[len(todo) + 1:], self._rcfg(beta=beta))
+        B = len(todo)
+        flat = torch.cat([out.reshape(-1), upd.to(torch.float32), its.to(torch.float32),
+                          status.to(torch.float32)]).cpu().numpy()                      # the step's single D2H
+        if flat[-1] != 0:
+            raise RuntimeError("bf_refine: capacity exceeded (views per box or polygon candidates)")
+        out_h, upd_h = flat[: 6 * B].reshape(B, 6), flat[6 * B: 7 * B]
+        self.last_iters = flat[7 * B: 8 * B].astype(np.int64)
+        # apply in map order; a box whose view set was fused earlier in this very call is skipped, exactly
+        # like the reference's sequential check_if_fusion (:634) would
+        rows = []
+        for k in range(B):
+            if box_manager.check_if_fusion(fl[todo[k]]):
+                continue
+            if upd_h[k] != 0:
+                rows.append(k)
+                box_manager.update_fusion_flag(todo[k])                                 # :723
+                box_manager.add_fusion_ind(fl[todo[k]])                                 # :724
+        if rows:
+            tgt = all_pred_box.pred_boxes_3d.tensor
+            idx = torch.as_tensor([todo[k] for k in rows], device=tgt.device)
+            src = out[torch.as_tensor(rows, device=out.device)] if tgt.is_cuda else torch.from_numpy(out_h[rows])
+            tgt[idx] = src.to(tgt.device)                                               # :721, in place

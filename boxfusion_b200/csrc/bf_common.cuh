@@ -1,0 +1,66 @@
+// Shared host-side plumbing of libboxfusion_sm100.so: the opaque handle, scratch arenas, error text.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/boxfusion_b200.h"
+
+enum {
+    BF_SCRATCH_PLANES_A = 0,  // double [M,12,4]
+    BF_SCRATCH_PLANES_B,      // double [N,12,4]
+    BF_SCRATCH_AABB_A,        // float  [M,6]
+    BF_SCRATCH_AABB_B,        // float  [N,6]
+    BF_SCRATCH_WORK,          // int2   work list of gate-passing pairs
+    BF_SCRATCH_COUNTERS,      // int64  [8]
+    BF_SCRATCH_MASK,          // uint32 NMS bit mask [N, W]
+    BF_SCRATCH_RANK,          // int32  [N]
+    BF_SCRATCH_IOU,           // double per work item
+    BF_SCRATCH_MISC,
+    BF_SCRATCH_REFINE,        // refine fitness / contributions
+    BF_SCRATCH_SLOTS
+};
+
+struct bf_handle {
+    int device;
+    int sm_count;
+    char err[512];
+    void* buf[BF_SCRATCH_SLOTS];
+    size_t cap[BF_SCRATCH_SLOTS];
+};
+
+static inline int bf_fail(bf_handle* h, int code, const char* what, const char* detail) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+
+#define BF_CUDA(h, expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) return bf_fail((h), BF_ERR_CUDA, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define BF_LAUNCH_CHECK(h, name)                                                           \
+    do {                                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess) return bf_fail((h), BF_ERR_CUDA, name, cudaGetErrorString(e__)); \
+    } while (0)
+
+// Grow-only scratch.  Growing frees the old block (cudaFree synchronises the device, so no kernel
+// can still be reading it).
+static inline int bf_scratch(bf_handle* h, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (h->cap[slot] < bytes) {
+        if (h->buf[slot]) BF_CUDA(h, cudaFree(h->buf[slot]));
+        h->buf[slot] = nullptr;
+        h->cap[slot] = 0;
+        size_t want = bytes + bytes / 2 + 4096;
+        BF_CUDA(h, cudaMalloc(&h->buf[slot], want));
+        h->cap[slot] = want;
+    }
+    *out = h->buf[slot];
+    return BF_OK;
+}
+
+static inline int bf_blocks(long long n, int threads) { return (int)((n + threads - 1) / threads); }

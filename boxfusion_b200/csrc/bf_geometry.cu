@@ -1,0 +1,136 @@
+// Box geometry kernels: corner generation (A1), camera->world lift (A2), observation projection (A15),
+// pose disparity (A8).  All float32 with the reference's rounding order made explicit through
+// __fmul_rn/__fadd_rn (torch's CPU bmm on 3x3 operands rounds as ((a0*b0 + a1*b1) + a2*b2), no FMA),
+// so results are bit-identical to the reference's CPU tensors.
+#include "bf_common.cuh"
+
+__device__ __forceinline__ float dot3_seq(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
+
+// boxes.py:725-778.  One thread per box: 15 floats in, 24 (+3) out.
+__global__ void bf_corners_kernel(const float* __restrict__ xyzlhw, const float* __restrict__ R, int N,
+                                  float* __restrict__ corners, float* __restrict__ centers) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* t = xyzlhw + 6 * n;
+    const float* r = R + 9 * n;
+    const float hl = t[3] * 0.5f, hh = t[4] * 0.5f, hw = t[5] * 0.5f;   // x/2 is exact
+    float r9[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r9[k] = r[k];
+    const float tx = t[0], ty = t[1], tz = t[2];
+    float sum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const float vx = ((v & 1) ^ ((v >> 1) & 1)) ? hl : -hl;        // v1,v2,v5,v6 -> +l/2
+        const float vy = (v & 2) ? hh : -hh;                            // v2,v3,v6,v7 -> +h/2
+        const float vz = (v & 4) ? hw : -hw;                            // v4..v7      -> +w/2
+        const float c0 = __fadd_rn(dot3_seq(r9[0], vx, r9[1], vy, r9[2], vz), tx);
+        const float c1 = __fadd_rn(dot3_seq(r9[3], vx, r9[4], vy, r9[5], vz), ty);
+        const float c2 = __fadd_rn(dot3_seq(r9[6], vx, r9[7], vy, r9[8], vz), tz);
+        corners[24 * n + 3 * v + 0] = c0;
+        corners[24 * n + 3 * v + 1] = c1;
+        corners[24 * n + 3 * v + 2] = c2;
+        sum[0] = v ? __fadd_rn(sum[0], c0) : c0;                        // np.mean(axis=1): sequential f32
+        sum[1] = v ? __fadd_rn(sum[1], c1) : c1;
+        sum[2] = v ? __fadd_rn(sum[2], c2) : c2;
+    }
+    if (centers) {
+        centers[3 * n + 0] = sum[0] * 0.125f;
+        centers[3 * n + 1] = sum[1] * 0.125f;
+        centers[3 * n + 2] = sum[2] * 0.125f;
+    }
+}
+
+extern "C" int bf_box_corners(bf_handle* h, const float* xyzlhw, const float* R, int N, float* corners,
+                              float* centers, void* stream) {
+    if (!h || N < 0 || (N > 0 && (!xyzlhw || !R || !corners))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_box_corners", "bad argument");
+    if (N == 0) return BF_OK;
+    bf_corners_kernel<<<bf_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, R, N, corners, centers);
+    BF_LAUNCH_CHECK(h, "bf_corners_kernel");
+    return BF_OK;
+}
+
+// boxes.py:825-833, in place.
+__global__ void bf_transform2world_kernel(float* __restrict__ xyzlhw, float* __restrict__ R,
+                                          const float* __restrict__ poses, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* p = poses + 16 * n;
+    float* t = xyzlhw + 6 * n;
+    float* r = R + 9 * n;
+    const float c0 = t[0], c1 = t[1], c2 = t[2];
+    float rb[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rb[k] = r[k];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a0 = p[4 * i], a1 = p[4 * i + 1], a2 = p[4 * i + 2];
+        t[i] = __fadd_rn(dot3_seq(a0, c0, a1, c1, a2, c2), p[4 * i + 3]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[3 * i + j] = dot3_seq(a0, rb[j], a1, rb[3 + j], a2, rb[6 + j]);
+    }
+}
+
+extern "C" int bf_transform2world(bf_handle* h, float* xyzlhw, float* R, const float* poses, int N, void* stream) {
+    if (!h || N < 0 || (N > 0 && (!xyzlhw || !R || !poses))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_transform2world", "bad argument");
+    if (N == 0) return BF_OK;
+    bf_transform2world_kernel<<<bf_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, R, poses, N);
+    BF_LAUNCH_CHECK(h, "bf_transform2world_kernel");
+    return BF_OK;
+}
+
+// instances.py:333-369.  One thread per corner.  pose_inv = inverse camera pose (world->camera).
+__global__ void bf_project_kernel(const float* __restrict__ corners, const float* __restrict__ pose_inv, int N,
+                                  float fx, float fy, float cx, float cy, float W, float H, float* __restrict__ uv) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * 8) return;
+    const int n = idx >> 3;
+    const float* p = pose_inv + 16 * n;
+    const float x = corners[3 * idx], y = corners[3 * idx + 1], z = corners[3 * idx + 2];
+    const float X = __fadd_rn(dot3_seq(p[0], x, p[1], y, p[2], z), p[3]);
+    const float Y = __fadd_rn(dot3_seq(p[4], x, p[5], y, p[6], z), p[7]);
+    const float Z = __fadd_rn(dot3_seq(p[8], x, p[9], y, p[10], z), p[11]);
+    float u = __fadd_rn(__fdiv_rn(__fmul_rn(fx, X), Z), cx);
+    float v = __fadd_rn(__fdiv_rn(__fmul_rn(fy, Y), Z), cy);
+    u = fminf(fmaxf(u, 0.f), W);                                          // torch.clamp(u, 0, W)
+    v = fminf(fmaxf(v, 0.f), H);
+    uv[2 * idx] = u;
+    uv[2 * idx + 1] = v;
+}
+
+extern "C" int bf_project_boxes(bf_handle* h, const float* corners, const float* pose_inv, int N, float fx, float fy,
+                                float cx, float cy, float W, float H, float* uv, void* stream) {
+    if (!h || N < 0 || (N > 0 && (!corners || !pose_inv || !uv))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_project_boxes", "bad argument");
+    if (N == 0) return BF_OK;
+    bf_project_kernel<<<bf_blocks(8LL * N, 128), 128, 0, (cudaStream_t)stream>>>(corners, pose_inv, N, fx, fy, cx, cy, W, H, uv);
+    BF_LAUNCH_CHECK(h, "bf_project_kernel");
+    return BF_OK;
+}
+
+// box_manager.py:168-186
+__global__ void bf_pose_disparity_kernel(const float* __restrict__ poses, const int32_t* __restrict__ ia,
+                                         const int32_t* __restrict__ ib, int n, float* __restrict__ baseline,
+                                         float* __restrict__ angle) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p1 = poses + 16 * ia[i];
+    const float* p2 = poses + 16 * ib[i];
+    const float dx = p2[3] - p1[3], dy = p2[7] - p1[7], dz = p2[11] - p1[11];
+    baseline[i] = sqrtf(dx * dx + dy * dy + dz * dz);
+    float tr = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) tr += p2[4 * r] * p1[4 * r] + p2[4 * r + 1] * p1[4 * r + 1] + p2[4 * r + 2] * p1[4 * r + 2];
+    const float c = fminf(fmaxf((tr - 1.f) * 0.5f, -1.f), 1.f);
+    angle[i] = acosf(c) * 180.f / 3.14159265358979323846f;
+}
+
+extern "C" int bf_pose_disparity(bf_handle* h, const float* poses, const int32_t* ia, const int32_t* ib, int n,
+                                 float* baseline, float* angle_deg, void* stream) {
+    if (!h || n < 0 || (n > 0 && (!poses || !ia || !ib || !baseline || !angle_deg))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_pose_disparity", "bad argument");
+    if (n == 0) return BF_OK;
+    bf_pose_disparity_kernel<<<bf_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(poses, ia, ib, n, baseline, angle_deg);
+    BF_LAUNCH_CHECK(h, "bf_pose_disparity_kernel");
+    return BF_OK;
+}

@@ -1,0 +1,192 @@
+"""Thin functional layer over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function here is a single call into libboxfusion_sm100.so (see include/boxfusion_b200.h for the
+reference interface each entry replaces).  Inputs living on the host are copied to the device; there
+is no alternative code path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IOU_ANALYTIC, IOU_SAMPLED_REF, RefineCfg, dev_tensor, handle, ptr
+
+FUSION_CAP = 32
+MAX_VIEWS = 64
+
+
+def _dev(device=None) -> torch.device:
+    if device is None or (isinstance(device, torch.device) and device.type != "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("boxfusion_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _pick_device(*tensors) -> torch.device:
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return _dev()
+
+
+def box_corners(xyzlhw, R, want_centers: bool = False):
+    """GeneralInstance3DBoxes.corners (boxes.py:725-778) -> [N,8,3] (and nms_3d's centres, instances.py:49)."""
+    dev = _pick_device(xyzlhw, R)
+    t = dev_tensor(xyzlhw, torch.float32, dev).reshape(-1, 6)
+    r = dev_tensor(R, torch.float32, dev).reshape(-1, 9)
+    n = t.shape[0]
+    corners = torch.empty((n, 8, 3), dtype=torch.float32, device=dev)
+    centers = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_centers else None
+    h = handle(dev)
+    h.check(h.lib.bf_box_corners(h.h, ptr(t), ptr(r), n, ptr(corners), ptr(centers), h.stream()), "bf_box_corners")
+    return (corners, centers) if want_centers else corners
+
+
+def transform2world_(xyzlhw: torch.Tensor, R: torch.Tensor, poses) -> None:
+    """GeneralInstance3DBoxes.transform2world (boxes.py:825-833), in place on CUDA tensors."""
+    assert xyzlhw.is_cuda and R.is_cuda and xyzlhw.is_contiguous() and R.is_contiguous()
+    p = dev_tensor(poses, torch.float32, xyzlhw.device).reshape(-1, 16)
+    h = handle(xyzlhw.device)
+    h.check(h.lib.bf_transform2world(h.h, ptr(xyzlhw), ptr(R), ptr(p), xyzlhw.shape[0], h.stream()), "bf_transform2world")
+
+
+def project_boxes(corners, pose_inv, K, W: float, H: float) -> torch.Tensor:
+    """Instances3D.project_3d_boxes (instances.py:333-369) given the inverted poses -> [N,8,2]."""
+    dev = _pick_device(corners)
+    c = dev_tensor(corners, torch.float32, dev).reshape(-1, 8, 3)
+    pi = dev_tensor(pose_inv, torch.float32, dev).reshape(-1, 16)
+    n = c.shape[0]
+    uv = torch.empty((n, 8, 2), dtype=torch.float32, device=dev)
+    h = handle(dev)
+    h.check(h.lib.bf_project_boxes(h.h, ptr(c), ptr(pi), n, float(K[0][0]), float(K[1][1]), float(K[0][2]),
+                                   float(K[1][2]), float(W), float(H), ptr(uv), h.stream()), "bf_project_boxes")
+    return uv
+
+
+def iou3d_matrix(cornersA, cornersB, mode: int = IOU_SAMPLED_REF, want_counts: bool = False, want_stats: bool = False):
+    """calculate_obb_iou / Instances3D.obb_iou for every pair (instances.py:106-125, 573-613) -> float64 [M,N]."""
+    dev = _pick_device(cornersA, cornersB)
+    a = dev_tensor(cornersA, torch.float32, dev).reshape(-1, 8, 3)
+    b = a if cornersB is cornersA else dev_tensor(cornersB, torch.float32, dev).reshape(-1, 8, 3)
+    M, N = a.shape[0], b.shape[0]
+    iou = torch.empty((M, N), dtype=torch.float64, device=dev)
+    counts = torch.empty((M, N, 3), dtype=torch.int32, device=dev) if want_counts else None
+    stats = torch.zeros(4, dtype=torch.int64, device=dev) if want_stats else None
+    h = handle(dev)
+    h.check(h.lib.bf_iou3d_matrix(h.h, ptr(a), M, ptr(b), N, int(mode), ptr(iou), ptr(counts), ptr(stats), h.stream()),
+            "bf_iou3d_matrix")
+    out = (iou,)
+    if want_counts:
+        out += (counts,)
+    if want_stats:
+        out += (stats,)
+    return out if len(out) > 1 else iou
+
+
+def nms3d(corners, centers, order, init_id, poses, fusion_list, fusion_len, fusion_flag, iou_threshold: float,
+          translation_gap: float, rotation_gap: float, center_gap: float = 0.5, mode: int = IOU_SAMPLED_REF):
+    """nms_3d + BoxManager.record (instances.py:22-101, box_manager.py:40-88).  All tensors on one CUDA device;
+    fusion_list [N,FUSION_CAP] / fusion_len [N] / fusion_flag [N] int32 are updated in place.
+    Returns (keep[N] int32 0/1, success[N] int32 0/1, status[1] int32) on the device."""
+    dev = corners.device
+    n = corners.shape[0]
+    keep = torch.empty(n, dtype=torch.int32, device=dev)
+    success = torch.empty(n, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    h = handle(dev)
+    h.check(h.lib.bf_nms3d(h.h, ptr(corners), ptr(centers), n, ptr(order), ptr(init_id), ptr(poses), poses.shape[0],
+                           ptr(fusion_list), ptr(fusion_len), ptr(fusion_flag), float(iou_threshold),
+                           float(translation_gap), float(rotation_gap), float(center_gap), int(mode),
+                           ptr(keep), ptr(success), ptr(status), h.stream()), "bf_nms3d")
+    return keep, success, status
+
+
+def corr2d(map_corners, small_mask, pose_inv, K, W: float, H: float, det_xyxy, want_boxes: bool = False):
+    """correspondence_association scoring (instances.py:446-468, 643-717) -> (best[n] int32, best_iou[n] f64)."""
+    dev = _pick_device(map_corners, det_xyxy)
+    mc = dev_tensor(map_corners, torch.float32, dev).reshape(-1, 8, 3)
+    sm = dev_tensor(small_mask, torch.int32, dev).reshape(-1)
+    pi = dev_tensor(pose_inv, torch.float32, dev).reshape(16)
+    det = dev_tensor(det_xyxy, torch.float32, dev).reshape(-1, 4)
+    G, n = mc.shape[0], det.shape[0]
+    best = torch.empty(n, dtype=torch.int32, device=dev)
+    best_iou = torch.empty(n, dtype=torch.float64, device=dev)
+    boxes2d = torch.empty((G, 4), dtype=torch.float64, device=dev) if want_boxes else None
+    h = handle(dev)
+    h.check(h.lib.bf_corr2d(h.h, ptr(mc), ptr(sm), G, ptr(pi), float(K[0][0]), float(K[1][1]), float(K[0][2]),
+                            float(K[1][2]), float(W), float(H), ptr(det), n, ptr(boxes2d), ptr(best), ptr(best_iou),
+                            h.stream()), "bf_corr2d")
+    return (best, best_iou, boxes2d) if want_boxes else (best, best_iou)
+
+
+def pose_disparity(poses, ia, ib):
+    """BoxManager.compute_pose_disparity (box_manager.py:168-186), batched -> (baseline[n], angle_deg[n])."""
+    dev = _pick_device(poses)
+    p = dev_tensor(poses, torch.float32, dev).reshape(-1, 16)
+    a = dev_tensor(ia, torch.int32, dev).reshape(-1)
+    b = dev_tensor(ib, torch.int32, dev).reshape(-1)
+    n = a.shape[0]
+    base = torch.empty(n, dtype=torch.float32, device=dev)
+    ang = torch.empty(n, dtype=torch.float32, device=dev)
+    h = handle(dev)
+    h.check(h.lib.bf_pose_disparity(h.h, ptr(p), ptr(a), ptr(b), n, ptr(base), ptr(ang), h.stream()), "bf_pose_disparity")
+    return base, ang
+
+
+def make_refine_cfg(cfg: dict, K16, img_h: float, img_w: float, beta: float = 0.9, early_stop: bool = True,
+                    max_hits: int = 200, iters: Optional[int] = None) -> RefineCfg:
+    bf = cfg["box_fusion"]
+    ro = bf["random_opt"]
+    K16 = np.asarray(K16, dtype=np.float32).reshape(-1)
+    return RefineCfg(int(bf["iters"] if iters is None else iters), int(bf["pst_size"]),
+                     float(ro["center_init_size"]), float(ro["shape_init_size"]),
+                     float(ro["center_scaling_coefficient"]), float(ro["shape_scaling_coefficient"]),
+                     float(beta), float(img_h), float(img_w),
+                     float(K16[0]), float(K16[2]), float(K16[5]), float(K16[6]), int(max_hits), int(bool(early_stop)))
+
+
+def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, view_index, rcfg: RefineCfg,
+           want_trace: bool = False):
+    """BoxFusion.boxfusion optimiser for B boxes in one launch (box_fusion.py:651-721).
+    Returns (out_xyzlhw[B,6] f32, updated[B] i32, iters[B] i32, trace|None, status[1] i32), all on the device."""
+    dev = _pick_device(per_xyzlhw, pst)
+    pst = dev_tensor(pst, torch.float32, dev).reshape(-1, 6)
+    t = dev_tensor(per_xyzlhw, torch.float32, dev).reshape(-1, 6)
+    r = dev_tensor(per_R, torch.float32, dev).reshape(-1, 9)
+    s = dev_tensor(per_scores, torch.float32, dev).reshape(-1)
+    uv = dev_tensor(per_uv, torch.float32, dev).reshape(-1, 16)
+    po = dev_tensor(per_poses, torch.float32, dev).reshape(-1, 16)
+    off = dev_tensor(view_offsets, torch.int32, dev).reshape(-1)
+    idx = dev_tensor(view_index, torch.int32, dev).reshape(-1)
+    B = off.shape[0] - 1
+    out = torch.empty((B, 6), dtype=torch.float32, device=dev)
+    upd = torch.empty(B, dtype=torch.int32, device=dev)
+    its = torch.empty(B, dtype=torch.int32, device=dev)
+    trace = torch.zeros((B, rcfg.iters, 8), dtype=torch.float32, device=dev) if want_trace else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    h = handle(dev)
+    h.check(h.lib.bf_refine(h.h, ptr(pst), pst.shape[0], ptr(t), ptr(r), ptr(s), ptr(uv), ptr(po), t.shape[0],
+                            ptr(off), ptr(idx), B, ctypes.byref(rcfg), ptr(out), ptr(upd), ptr(its), ptr(trace),
+                            ptr(status), h.stream()), "bf_refine")
+    return out, upd, its, trace, status
+
+
+def evaluate_iou(pst, box6, rot9, uv, poses, search6, rcfg: RefineCfg) -> torch.Tensor:
+    """BoxFusion.evaluate_iou (box_fusion.py:413-461) -> fitness[P] float32 on the device."""
+    dev = _pick_device(pst, uv)
+    pst = dev_tensor(pst, torch.float32, dev).reshape(-1, 6)
+    b = dev_tensor(np.asarray(box6, dtype=np.float32) if not isinstance(box6, torch.Tensor) else box6, torch.float32, dev).reshape(6)
+    r = dev_tensor(rot9, torch.float32, dev).reshape(9)
+    u = dev_tensor(uv, torch.float32, dev).reshape(-1, 16)
+    p = dev_tensor(poses, torch.float32, dev).reshape(-1, 16)
+    s = dev_tensor(search6, torch.float32, dev).reshape(6)
+    fit = torch.empty(pst.shape[0], dtype=torch.float32, device=dev)
+    h = handle(dev)
+    h.check(h.lib.bf_evaluate_iou(h.h, ptr(pst), pst.shape[0], ptr(b), ptr(r), ptr(u), ptr(p), u.shape[0], ptr(s),
+                                  ctypes.byref(rcfg), ptr(fit), h.stream()), "bf_evaluate_iou")
+    return fit

@@ -1,0 +1,143 @@
+/* boxfusion_b200 - C ABI of the B200-native (sm_100a) multi-view box-fusion hot path.
+ *
+ * One shared library, `libboxfusion_sm100.so`; plain pointers and sizes only (no torch types).
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * tree pliam1105/BoxFusion; see SURVEY.md section 8(a) for the row ids A1..A22).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless the parameter is documented "host".
+ *   - Callers own every buffer; the library borrows them for the duration of the call and keeps
+ *     only its own scratch inside the opaque handle.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous with respect to the host
+ *     unless documented otherwise.  One handle per device; a handle is not re-entrant.
+ *   - Return value: BF_OK (0) or a negative BF_ERR_*; bf_last_error(h) gives the text.
+ *   - There is no CPU fallback: bf_create fails (BF_ERR_CUDA) when the device is not sm_100.
+ *   - Row-major float32 unless stated; boxes are (x,y,z,l,h,w) with l<->X, h<->Y, w<->Z of the box
+ *     frame and R[9] row-major (boxes.py:725-778); poses are camera->world 4x4 row-major
+ *     (box_fusion.py:348-354).
+ */
+#ifndef BOXFUSION_B200_H
+#define BOXFUSION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bf_handle bf_handle;
+
+enum {
+    BF_OK = 0,
+    BF_ERR_INVALID_ARG = -1,
+    BF_ERR_CUDA = -2,
+    BF_ERR_CAPACITY = -3   /* a fixed-capacity structure overflowed (fusion list, polygon buffer, work list) */
+};
+
+/* IoU estimator of bf_iou3d_*  */
+enum {
+    BF_IOU_SAMPLED_REF = 0, /* reference-exact: containment gate + 25^3 grid counts (instances.py:514-613) */
+    BF_IOU_ANALYTIC = 1     /* gravity-aligned BEV Sutherland-Hodgman clip x height overlap; pairs without a
+                               shared box axis fall back (on the GPU) to BF_IOU_SAMPLED_REF */
+};
+
+#define BF_FUSION_CAP 32    /* max observations per fusion list held on the device (box_manager.py:13) */
+#define BF_MAX_VIEWS 64     /* max views of one box in bf_refine */
+#define BF_MAX_PARTICLES 4096
+
+int bf_version(void);
+int bf_create(int device, bf_handle** out);
+void bf_destroy(bf_handle* h);
+const char* bf_last_error(bf_handle* h);
+int bf_fusion_cap(void);
+
+/* ---- A1  GeneralInstance3DBoxes.corners (boxes.py:725-778) ------------------------------------
+ * corners[n][v][3], vertex order v0..v7 of the reference; centers (optional) = mean of the 8 corners
+ * as nms_3d computes them (instances.py:49). */
+int bf_box_corners(bf_handle* h, const float* xyzlhw /*[N,6]*/, const float* R /*[N,9]*/, int N,
+                   float* corners /*[N,8,3]*/, float* centers /*[N,3] or NULL*/, void* stream);
+
+/* ---- A2  GeneralInstance3DBoxes.transform2world (boxes.py:825-833), in place -------------------- */
+int bf_transform2world(bf_handle* h, float* xyzlhw /*[N,6]*/, float* R /*[N,9]*/, const float* poses /*[N,16]*/,
+                       int N, void* stream);
+
+/* ---- A15 Instances3D.project_3d_boxes (instances.py:333-369) -----------------------------------
+ * Observation corners in each detection's own camera, clamped to [0,W]x[0,H].  The reference
+ * inverts the pose with a general LU (torch.linalg.inv); this uses the rigid inverse R^T(p-t). */
+int bf_project_boxes(bf_handle* h, const float* corners /*[N,8,3]*/, const float* poses /*[N,16]*/, int N,
+                     float fx, float fy, float cx, float cy, float W, float H, float* uv /*[N,8,2]*/, void* stream);
+
+/* ---- A3/A4  Instances3D.obb_iou / calculate_obb_iou (instances.py:106-125, 573-613) -------------
+ * IoU of every (a in A) x (b in B) from corner arrays.  iou is float64 like the reference's;
+ * counts (optional) receives {count1,count2,common} of the 25^3 estimator (zeros when the gate
+ * fails or the analytic path was taken).  stats (optional, 4 x int64, device): pairs, AABB-passing
+ * pairs, gate-passing pairs, analytic pairs. */
+int bf_iou3d_matrix(bf_handle* h, const float* cornersA /*[M,8,3]*/, int M, const float* cornersB /*[N,8,3]*/, int N,
+                    int mode, double* iou /*[M,N]*/, int32_t* counts /*[M,N,3] or NULL*/, int64_t* stats /*[4] or NULL*/,
+                    void* stream);
+
+/* ---- A5/A6/A7/A8  nms_3d + BoxManager.record (instances.py:22-101, box_manager.py:40-88,188-215)
+ * Greedy score-ordered 3-D NMS over N boxes with the fusion-list bookkeeping of record().
+ *   order      [N] int32: box indices by descending score (scores.argsort()[::-1])
+ *   init_id    [N] int32: per-frame observation index of each box (instances.py:53)
+ *   poses      [M,16]: per-frame camera poses indexed by the values stored in the fusion lists
+ *   fusion_list[N,BF_FUSION_CAP] / fusion_len[N] / fusion_flag[N] (int32): in/out, rows kept sorted
+ * outputs (int32, device): keep[N] 0/1, success[N] 0/1 (heads that suppressed something; valid_num += 1),
+ *   status[1]: 0 or BF_ERR_CAPACITY if a fusion list overflowed BF_FUSION_CAP.
+ * IoU uses `mode`; suppression is `iou > iou_threshold` evaluated in float64. */
+int bf_nms3d(bf_handle* h, const float* corners /*[N,8,3]*/, const float* centers /*[N,3]*/, int N,
+             const int32_t* order, const int32_t* init_id, const float* poses, int M,
+             int32_t* fusion_list, int32_t* fusion_len, int32_t* fusion_flag,
+             double iou_threshold, float translation_gap, float rotation_gap_deg, float center_gap, int mode,
+             int32_t* keep, int32_t* success, int32_t* status, void* stream);
+
+/* ---- A9-A12  correspondence_association core (instances.py:446-483, 643-717; box_manager.py:90-129)
+ * For each of n_small detections (2-D boxes det_xyxy, float32) project the G candidate map boxes
+ * (corners, float32) with pose_inv (row-major 4x4 float32, already inverted by the caller exactly as
+ * the reference does with np.linalg.inv) and K, form the clipped 2-D AABB of corners with 0<Z<8
+ * (float64), IoU against the detection (float64, +1e-6), zero rows whose map box is not small
+ * (small_mask[G] int32), and return the first arg-max and its IoU per detection. */
+int bf_corr2d(bf_handle* h, const float* map_corners /*[G,8,3]*/, const int32_t* small_mask /*[G]*/, int G,
+              const float* pose_inv /*[16]*/, float fx, float fy, float cx, float cy, float W, float H,
+              const float* det_xyxy /*[n_small,4]*/, int n_small,
+              double* boxes2d /*[G,4] or NULL*/, int32_t* best /*[n_small]*/, double* best_iou /*[n_small]*/, void* stream);
+
+/* ---- A8  BoxManager.compute_pose_disparity (box_manager.py:168-186), batched ------------------- */
+int bf_pose_disparity(bf_handle* h, const float* poses /*[M,16]*/, const int32_t* ia, const int32_t* ib, int n,
+                      float* baseline /*[n]*/, float* angle_deg /*[n]*/, void* stream);
+
+/* ---- A16-A22  BoxFusion.boxfusion optimiser (box_fusion.py:264-405, 413-600, 651-721) ----------
+ * Refines B map boxes independently; box b fuses the observations view_index[view_offsets[b] ..
+ * view_offsets[b+1]) (CSR, int32) of the per-frame store.  All `iters` optimiser iterations run
+ * inside one launch.  Float32 arithmetic with the same operation order as the reference kernel
+ * (compiled without FMA contraction), line intersections in float64, global box state in float64.
+ */
+typedef struct {
+    int32_t iters;            /* box_fusion.iters (20)                                   */
+    int32_t pst_size;         /* box_fusion.pst_size; particles >= 32*(pst_size/32) score 0 */
+    float center_init, shape_init;      /* random_opt.*_init_size                          */
+    float center_scale, shape_scale;    /* random_opt.*_scaling_coefficient                */
+    double beta;              /* 0.9                                                     */
+    float img_h, img_w;       /* BoxFusion.H / .W after update_intrinsics                */
+    float fx, cx, fy, cy;     /* K[0],K[2],K[5],K[6] of the flattened 4x4 (box_fusion.py:356-357) */
+    int32_t max_hits;         /* 200                                                     */
+    int32_t early_stop;       /* 1: stop after 3 consecutive failures (reference); 0: run all iters */
+} bf_refine_cfg;
+
+int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,
+              const float* per_xyzlhw /*[M,6]*/, const float* per_R /*[M,9]*/, const float* per_scores /*[M]*/,
+              const float* per_uv /*[M,16]*/, const float* per_poses /*[M,16]*/, int M,
+              const int32_t* view_offsets /*[B+1]*/, const int32_t* view_index /*[sum V]*/, int B,
+              const bf_refine_cfg* cfg /*host*/,
+              float* out_xyzlhw /*[B,6]*/, int32_t* out_updated /*[B]*/, int32_t* out_iters /*[B]*/,
+              float* trace /*[B,iters,8] or NULL: success,min_iou,search[6]*/, int32_t* status /*[1]*/, void* stream);
+
+/* BoxFusion.evaluate_iou (box_fusion.py:413-461): one fitness vector for one box (test/diagnostic entry). */
+int bf_evaluate_iou(bf_handle* h, const float* pst /*[P,6]*/, int P, const float* box6 /*[6]*/, const float* rot9,
+                    const float* uv /*[V,16]*/, const float* poses /*[V,16]*/, int V, const float* search6,
+                    const bf_refine_cfg* cfg /*host*/, float* fitness /*[P]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOXFUSION_B200_H */

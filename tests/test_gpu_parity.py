@@ -1,0 +1,321 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(libboxfusion_sm100.so via boxfusion_b200.ops / the reference-shaped API) and is compared with
+(a) golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Bars: integer / index outputs and sampled-IoU counts bit-exact; refinement float32 outputs bit-exact
+(the kernel reproduces the reference's operation order); analytic IoU within 1e-9 of the float64
+CPU restatement of the same definition."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from boxfusion_b200 import ops, api                      # noqa: E402
+from boxfusion_b200.driver import FusionSession          # noqa: E402
+from boxfusion_b200.synthetic import (SyntheticScene, make_cfg, make_pst, map_and_detections, random_boxes,  # noqa: E402
+                                      refine_problem)
+from oracle import port, refine_oracle as ro, analytic_oracle   # noqa: E402
+from tests.golden.make_golden import SEQUENCES           # noqa: E402
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8) if a.dtype.kind == "f" else a
+
+
+def _corners_cpu(t, R):
+    return port.GeneralInstance3DBoxes(torch.from_numpy(t), torch.from_numpy(R)).corners.numpy()
+
+
+# ---- A1/A2/A15 geometry ------------------------------------------------------------------------------
+
+def test_corners_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "iou_pairs.npz"))
+    c, cen = ops.box_corners(g["tensor"], g["R"], want_centers=True)
+    assert np.array_equal(_bits(c.cpu().numpy()), _bits(g["corners"]))
+    assert np.array_equal(_bits(cen.cpu().numpy()), _bits(np.mean(g["corners"], axis=1)))
+    t, R = random_boxes(5000, 3, tilt_noise=0.03)
+    assert np.array_equal(_bits(ops.box_corners(t, R).cpu().numpy()), _bits(_corners_cpu(t, R)))
+
+
+def test_lift_and_project_match_reference_golden(golden_dir):
+    name = "seq_scannet_tilt"
+    spec = dict(SEQUENCES[name]); spec.pop("frames")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    scene = SyntheticScene(**spec)
+    cfg = make_cfg(spec["shape"], pst_path=os.path.join(golden_dir, "pst_1024_0.npy"))
+    for device in ("cuda", "cpu"):
+        sess = FusionSession(api, cfg, device=device)
+        for k in range(3):
+            ins, _ = sess.make_pred_instances(scene.keyframe(k))
+            assert np.array_equal(_bits(ins.pred_boxes_3d.tensor.cpu().numpy()), _bits(g[f"k{k}_tensor_w"]))
+            assert np.array_equal(_bits(ins.pred_boxes_3d.R.cpu().numpy()), _bits(g[f"k{k}_R_w"]))
+            got, ref = ins.projected_boxes.cpu().numpy(), g[f"k{k}_projected"]
+            np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-4)
+
+
+# ---- A3/A4 oriented-3D IoU --------------------------------------------------------------------------
+
+def test_sampled_iou_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "iou_pairs.npz"))
+    iou = ops.iou3d_matrix(g["corners"], g["corners"]).cpu().numpy()
+    assert np.array_equal(iou[g["ia"], g["ib"]], g["iou"])            # float64, exact, all 3486 pairs
+    assert np.array_equal(iou[g["ib"], g["ia"]], g["iou"])            # symmetric
+    m = ops.iou3d_matrix(g["ov_a"], g["ov_b"]).cpu().numpy()
+    assert np.array_equal(np.diagonal(m), g["ov_iou"])
+
+
+def test_sampled_counts_match_c_oracle_large():
+    (mt, mR, _), (dt, dR, _) = map_and_detections(600, 150, seed=4, tilt_noise=0.02)
+    ca, cb = _corners_cpu(dt, dR), _corners_cpu(mt, mR)
+    iou, cnt, stats = ops.iou3d_matrix(ca, cb, want_counts=True, want_stats=True)
+    iou, cnt, stats = iou.cpu().numpy(), cnt.cpu().numpy(), stats.cpu().numpy()
+    ia, ib = np.meshgrid(np.arange(150), np.arange(600), indexing="ij")
+    gate, ref = port.obb_counts_pairs_c(np.concatenate([ca, cb]), ia.ravel(), ib.ravel() + 150)
+    ref = ref.reshape(150, 600, 3)
+    assert np.array_equal(cnt, ref)
+    assert np.array_equal(iou, np.where(gate.reshape(150, 600) > 0, port.iou_from_counts(ref), 0.0))
+    assert stats[0] == 150 * 600 and stats[2] == int(gate.sum()) and stats[1] >= stats[2]
+    assert gate.sum() > 50
+
+
+def test_iou_edge_cases():
+    t, R = random_boxes(3, 1)
+    c = _corners_cpu(t, R)
+    assert ops.iou3d_matrix(c[:0], c).shape == (0, 3)
+    one = ops.iou3d_matrix(c[:1], c[:1], want_counts=True)
+    assert one[0].shape == (1, 1) and one[0][0, 0].item() > 0.99           # identical boxes
+    far = c.copy(); far[..., 0] += 100.0
+    assert float(ops.iou3d_matrix(c, far).abs().max()) == 0.0
+    assert api.Instances3D.obb_iou(c[0], c[0]) == port.iou_from_counts(port.obb_counts_c(c[0], c[0])[1])
+    v = api.calculate_obb_iou(c[0], c)
+    assert v.shape == (3,) and v.dtype == np.float64
+
+
+def test_analytic_iou_matches_fp64_oracle():
+    (mt, mR, _), (dt, dR, _) = map_and_detections(400, 120, seed=9, tilt_noise=0.0)
+    ca, cb = _corners_cpu(dt, dR), _corners_cpu(mt, mR)
+    iou, stats = ops.iou3d_matrix(ca, cb, mode=ops.IOU_ANALYTIC, want_stats=True)
+    iou, stats = iou.cpu().numpy(), stats.cpu().numpy()
+    ref = analytic_oracle.iou_matrix(ca, cb)
+    np.testing.assert_allclose(iou, ref, rtol=1e-9, atol=1e-12)
+    assert (ref > 0.1).sum() > 40 and stats[3] == stats[1]               # every AABB-passing pair was co-axial
+    # sampled estimator agrees with the analytic value to its discretisation error (<= 0.036 abs)
+    samp = ops.iou3d_matrix(ca, cb).cpu().numpy()
+    both = (ref > 0) & (samp > 0)
+    assert np.abs(ref - samp)[both].max() < 0.06
+
+
+def test_analytic_falls_back_to_sampled_for_tilted_boxes():
+    (mt, mR, _), (dt, dR, _) = map_and_detections(200, 80, seed=10, tilt_noise=0.05)
+    ca, cb = _corners_cpu(dt, dR), _corners_cpu(mt, mR)
+    a, stats = ops.iou3d_matrix(ca, cb, mode=ops.IOU_ANALYTIC, want_stats=True)
+    s = ops.iou3d_matrix(ca, cb).cpu().numpy()
+    assert int(stats[3]) == 0                                            # no co-axial pair -> all sampled
+    assert np.array_equal(a.cpu().numpy(), s)
+
+
+# ---- A5-A8 NMS + record -------------------------------------------------------------------------------
+
+def _nms_case(n_map, n_det, seed, tilt=0.01):
+    (mt, mR, ms), (dt, dR, ds) = map_and_detections(n_map, n_det, seed=seed, tilt_noise=tilt)
+    t, R, s = np.concatenate([mt, dt]), np.concatenate([mR, dR]), np.concatenate([ms, ds])
+    rs = np.random.RandomState(seed)
+    n = n_map + n_det
+    # per-frame store: every map box has 1..4 earlier observations with random camera poses
+    lists, M = [], 0
+    for i in range(n):
+        k = 1 if i >= n_map else int(rs.choice([1, 1, 2, 3, 4]))
+        lists.append(list(range(M, M + k))); M += k
+    poses = np.tile(np.eye(4, dtype=np.float32), (M, 1, 1))
+    from scipy.spatial.transform import Rotation as Rot
+    poses[:, :3, :3] = Rot.from_euler("z", rs.uniform(0, 90, M), degrees=True).as_matrix().astype(np.float32)
+    poses[:, :3, 3] = rs.uniform(-1.5, 1.5, (M, 3)).astype(np.float32)
+    init_id = np.array([l[0] for l in lists], dtype=np.int64)
+    flags = [int(rs.rand() < 0.2) if len(l) > 1 else 0 for l in lists]
+    return t, R, s, lists, flags, poses, init_id
+
+
+def _run_nms(impl, case, thr=0.1):
+    t, R, s, lists, flags, poses, init_id = case
+    cfg = make_cfg("ca1m", pst_path=make_pst(32))
+    bm = impl.BoxManager(cfg)
+    bm.fusion_list = [list(l) for l in lists]
+    bm.fusion_flag = list(flags)
+    ins = impl.Instances3D((512, 384))
+    ins.pred_boxes_3d = impl.GeneralInstance3DBoxes(torch.from_numpy(t), torch.from_numpy(R))
+    ins.scores = torch.from_numpy(s)
+    ins.init_id = torch.from_numpy(init_id)
+    ins.valid_num = torch.zeros(len(s))
+    keep, succ = impl.Instances3D.spatial_association(ins, thr, bm, torch.from_numpy(poses))
+    return ([int(k) for k in keep], [int(k) for k in succ], [[int(x) for x in l] for l in bm.fusion_list],
+            list(bm.fusion_flag), ins.valid_num.numpy().copy())
+
+
+@pytest.mark.parametrize("n_map,n_det,seed", [(200, 50, 1), (60, 40, 2), (400, 100, 3)])
+def test_nms_matches_port(n_map, n_det, seed, monkeypatch):
+    monkeypatch.setattr(port, "IOU_BACKEND", "c")
+    case = _nms_case(n_map, n_det, seed)
+    got, ref = _run_nms(api, case), _run_nms(port, case)
+    assert got[0] == ref[0] and got[1] == ref[1]                       # keep / success indices bit-exact
+    assert got[2] == ref[2] and got[3] == ref[3]                       # fusion lists and flags
+    assert np.array_equal(got[4], ref[4])
+    assert len(ref[1]) > 10 and any(len(l) > 2 for l in ref[2])
+
+
+def test_nms_single_box_quirk():
+    case = _nms_case(1, 0, 5)
+    cfg = make_cfg("ca1m", pst_path=make_pst(32))
+    ins = api.Instances3D((512, 384))
+    ins.pred_boxes_3d = api.GeneralInstance3DBoxes(torch.from_numpy(case[0]), torch.from_numpy(case[1]))
+    ins.scores = torch.from_numpy(case[2])
+    assert api.Instances3D.spatial_association(ins, 0.1, api.BoxManager(cfg), None) is ins   # instances.py:381-382
+
+
+# ---- A9-A12 correspondence ------------------------------------------------------------------------------
+
+def test_corr2d_matches_port():
+    rs = np.random.RandomState(3)
+    t, R = random_boxes(120, 8, side=6.0)
+    corners = _corners_cpu(t, R)
+    from boxfusion_b200.synthetic import look_at_pose
+    pose = look_at_pose(np.array([4.0, 0.5, 1.2]), np.array([0.0, 0.0, 0.8])).astype(np.float32)
+    cfg = make_cfg("scannet")
+    cam = cfg["cam"]
+    K = np.array([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]], dtype=np.float32)
+    W, H = cam["W"], cam["H"]
+    ref_boxes = port.Instances3D.project_3d_to_2d_box(corners, K, pose, H, W)
+    got_boxes = api.Instances3D.project_3d_to_2d_box(corners, K, pose, H, W)
+    np.testing.assert_allclose(got_boxes, ref_boxes, rtol=1e-12, atol=1e-9)
+    assert (ref_boxes.sum(1) > 0).sum() > 10
+    det = np.stack([rs.uniform(0, 300, 40), rs.uniform(0, 200, 40), rs.uniform(320, 640, 40), rs.uniform(220, 480, 40)], 1).astype(np.float32)
+    small = (np.max(t[:, 3:], axis=1) < 0.6).astype(np.int32)
+    best, best_iou = ops.corr2d(corners, small, np.linalg.inv(pose), K, W, H, det)
+    for k in range(40):
+        iou = port.Instances3D.IoU_2D_box(det[k], ref_boxes) * small
+        assert int(best[k]) == int(np.argmax(iou))
+        assert abs(float(best_iou[k]) - iou.max()) < 1e-12
+
+
+# ---- A16-A22 refinement ----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("V", [3, 5, 8])
+def test_refine_matches_reference_golden(golden_dir, V):
+    g = np.load(os.path.join(golden_dir, "refine_cases.npz"))
+    pst = np.load(os.path.join(golden_dir, "pst_1024_0.npy"))
+    cfg = make_cfg("ca1m", pst_path=pst, pst_size=1024)
+    W, H = (int(x) for x in g[f"v{V}_size"])
+    T, R, S, P, proj = (g[f"v{V}_{k}"] for k in ("tensor", "R", "scores", "poses", "projected"))
+    bf = api.BoxFusion(cfg)
+    bf.update_intrinsics((W, H), g[f"v{V}_K"])
+    B = T.shape[0]
+    search = np.array([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], np.float32)
+    for b in range(B):
+        fit = bf.evaluate_iou(T[b, 0].astype(np.float64), proj[b], R[b, 0], S[b], P[b], search, V)
+        assert np.array_equal(_bits(fit), _bits(g[f"v{V}_fitness0"][b]))      # float32 fitness, bit-exact
+    allp = api.Instances3D((H, W))
+    allp.pred_boxes_3d = api.GeneralInstance3DBoxes(torch.from_numpy(T[:, 0].copy()), torch.from_numpy(R[:, 0].copy()))
+    per = api.Instances3D((H, W))
+    per.pred_boxes_3d = api.GeneralInstance3DBoxes(torch.from_numpy(T.reshape(-1, 6)), torch.from_numpy(R.reshape(-1, 3, 3)))
+    per.cam_pose = torch.from_numpy(P.reshape(-1, 4, 4))
+    per.scores = torch.from_numpy(S.reshape(-1))
+    per.projected_boxes = torch.from_numpy(proj.reshape(-1, 8, 2))
+    bm = api.BoxManager(cfg)
+    bm.fusion_list = [list(range(b * V, (b + 1) * V)) for b in range(B)]
+    bm.fusion_flag = [0] * B
+    bf.boxfusion(allp, per, bm)
+    assert np.array_equal(_bits(allp.pred_boxes_3d.tensor.numpy()), _bits(g[f"v{V}_fused"]))   # fused boxes bit-exact
+    assert bm.fusion_flag == [int(x) for x in g[f"v{V}_flag"]]
+    assert bm.already_fusion == bm.fusion_list
+
+
+@pytest.mark.parametrize("B,V,P,pst_size", [(12, 8, 512, 512), (6, 32, 1024, 1024), (5, 4, 500, 500), (3, 64, 256, 256)])
+def test_refine_matches_c_oracle(B, V, P, pst_size):
+    prob = refine_problem(B, V, seed=B * 100 + V)
+    W, H = prob["size"]
+    pst = make_pst(P, seed=1)
+    cfg = make_cfg("ca1m", pst_path=pst, pst_size=pst_size)
+    K16 = ro.K16_from_K3(prob["K"])
+    corners = ops.box_corners(prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 3, 3))
+    proj = ops.project_boxes(corners, torch.linalg.inv(torch.from_numpy(prob["poses"].reshape(-1, 4, 4))), prob["K"], W, H)
+    proj_h = proj.cpu().numpy().reshape(B, V, 16)
+    rcfg = ops.make_refine_cfg(cfg, K16, H, W)
+    off = np.arange(B + 1, dtype=np.int32) * V
+    idx = np.arange(B * V, dtype=np.int32)
+    out, upd, its, trace, status = ops.refine(pst, prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 9),
+                                              prob["scores"].reshape(-1), proj, prob["poses"].reshape(-1, 16), off, idx,
+                                              rcfg, want_trace=True)
+    assert int(status.item()) == 0
+    out, upd, its, trace = out.cpu().numpy(), upd.cpu().numpy(), its.cpu().numpy(), trace.cpu().numpy()
+    cs = ro.make_cfg_struct(cfg, H, W)
+    for b in range(B):
+        u, o6, n_it, tr = ro.refine_box(prob["tensor"][b], prob["R"][b], prob["scores"][b], proj_h[b], prob["poses"][b],
+                                        pst, K16, cs, want_trace=True)
+        assert bool(upd[b]) == u and int(its[b]) == n_it
+        assert np.array_equal(_bits(trace[b, :n_it]), _bits(tr[:n_it]))       # per-iteration success/min_iou/search radii
+        if u:
+            assert np.array_equal(_bits(out[b]), _bits(o6))
+
+
+def test_refine_empty_and_capacity():
+    pst = make_pst(64)
+    cfg = make_cfg("ca1m", pst_path=pst, pst_size=64)
+    rcfg = ops.make_refine_cfg(cfg, ro.K16_from_K3(np.eye(3)), 512, 384)
+    z = np.zeros((1, 6), np.float32)
+    out, upd, its, _, status = ops.refine(pst, z, np.zeros((1, 9), np.float32), np.zeros(1, np.float32),
+                                          np.zeros((1, 16), np.float32), np.zeros((1, 16), np.float32),
+                                          np.zeros(1, np.int32), np.zeros(0, np.int32), rcfg)
+    assert out.shape == (0, 6) and int(status.item()) == 0
+    # 65 views > BF_MAX_VIEWS is reported, not silently truncated
+    n = 65
+    _, _, _, _, status = ops.refine(pst, np.zeros((n, 6), np.float32), np.zeros((n, 9), np.float32), np.zeros(n, np.float32),
+                                    np.zeros((n, 16), np.float32), np.zeros((n, 16), np.float32),
+                                    np.array([0, n], np.int32), np.arange(n, dtype=np.int32), rcfg)
+    assert int(status.item()) == -3
+
+
+# ---- whole keyframe sequences through the reference-shaped API ------------------------------------------
+
+@pytest.mark.parametrize("name", list(SEQUENCES))
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_sequence_matches_reference_golden(golden_dir, name, device):
+    spec = dict(SEQUENCES[name])
+    n_frames = spec.pop("frames")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    scene = SyntheticScene(**spec)
+    cfg = make_cfg(spec["shape"], pst_path=os.path.join(golden_dir, "pst_1024_0.npy"), pst_size=1024)
+    sess = FusionSession(api, cfg, device=device)
+    for k in range(n_frames):
+        kf = scene.keyframe(k)
+        ins, pose_np = sess.pred_instances_from_world(kf, g[f"k{k}_tensor_w"], g[f"k{k}_R_w"], g[f"k{k}_projected"])
+        sess.step(kf, ins, pose_np)
+        snap = sess.snapshot()
+        for key, val in snap.items():
+            ref = g[f"k{k}_snap_{key}"]
+            assert val.shape == ref.shape and np.array_equal(_bits(val), _bits(ref)), (name, k, key)
+        if sess.last_mask is not None:
+            assert sess.last_mask == [int(x) for x in g[f"k{k}_mask"]]
+            assert sess.last_success == [int(x) for x in g[f"k{k}_success"]]
+            sess.last_mask = sess.last_success = None
+
+
+def test_sequence_matches_port_longer(monkeypatch):
+    """A denser 20-keyframe CA-1M-shaped sequence against the CPU port run live (not golden)."""
+    monkeypatch.setattr(port, "IOU_BACKEND", "c")
+    scene = SyntheticScene(n_objects=120, seed=7, max_det=40, shape="ca1m", tilt_noise=0.01)
+    pst = make_pst(512, seed=0)
+    cfg = make_cfg("ca1m", pst_path=pst, pst_size=512)
+    a, b = FusionSession(api, cfg, device="cuda"), FusionSession(port, cfg)
+    for k in range(20):
+        kf = scene.keyframe(k)
+        ins_b, pose_np = b.make_pred_instances(kf)
+        ins_a, _ = a.pred_instances_from_world(kf, ins_b.pred_boxes_3d.tensor.numpy(), ins_b.pred_boxes_3d.R.numpy(),
+                                               ins_b.projected_boxes.numpy())
+        a.step(kf, ins_a, pose_np); b.step(kf, ins_b, pose_np)
+        sa, sb = a.snapshot(), b.snapshot()
+        for key in sa:
+            assert sa[key].shape == sb[key].shape and np.array_equal(_bits(sa[key]), _bits(sb[key])), (k, key)
+    assert len(b.box_manager.already_fusion) > 20
