@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py - BoxFusion multi-view box-fusion hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one keyframe of the synthetic CA-1M-shaped sequence (BASELINE.json configs[1]): camera->world
+lift + observation projection (A2/A15) + 3-D NMS association with fusion-list bookkeeping (A3-A8) + small-
+object correspondence (A9-A12) + particle refinement of every fusable map box (A16-A22), replayed through the
+reference-shaped API exactly as demo.py:200-327 calls it (boxfusion_b200/driver.py).
+
+Printed JSON line (rank 0):
+  value        whole-job keyframes/s with every keyframe's detections already resident in HBM
+  e2e          the same metric with HOST (pinned) detections copied in and results read back inside the timed region
+  ms_per_step  mean CUDA-event time of one keyframe (HBM-resident pass)
+  roofline     dominant kernel (bf_refine_kernel): algorithmic FP32 flops / CUDA-event duration vs the FP32 FMA
+               throughput measured on this device (bf_probe_fp32); the path is FP32-issue bound, not HBM or tensor
+               (SURVEY.md section 8(d)); achieved HBM GB/s is reported beside it
+  cpu_baseline the CPU port of the reference algorithm (oracle/port.py, scipy/Qhull IoU + C kernel) on a bounded prefix
+Multi-GPU: independent sequences, one per rank (weak scaling), no data-path collective; a final NCCL all_gather
+collects the per-rank maps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from boxfusion_b200.synthetic import SyntheticScene, make_cfg          # noqa: E402
+from boxfusion_b200.driver import FusionSession                         # noqa: E402
+
+GOLDEN_PST = os.path.join(ROOT, "tests", "golden", "pst_1024_0.npy")
+FRAMES_PER_SEQUENCE = 300
+N_OBJECTS, MAX_DET = 200, 50
+# algorithmic FP32 work of one (particle, view) evaluation of compute_iou_value, counted on the straight-line
+# path of bf_eval_view for two hexagonal hulls with 6 intersection candidates (DESIGN.md section "Kernels")
+FLOP_PER_EVAL = 1900.0
+# bytes one evaluation must touch: nothing in HBM (PST row and view constants are on chip); 4 B of fitness per particle
+BYTES_PER_EVAL = 0.5
+
+
+def scene_for(rank_seed: int) -> SyntheticScene:
+    return SyntheticScene(n_objects=N_OBJECTS, seed=rank_seed, max_det=MAX_DET, shape="ca1m")
+
+
+def build_keyframes(seed: int, n: int):
+    sc = scene_for(seed)
+    return [sc.keyframe(k) for k in range(n)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pin_keyframe(kf):
+    """Host (pinned) staging of one keyframe's detections: what the e2e pass copies in every step."""
+    kf._pinned = {k: torch.from_numpy(getattr(kf, k)).pin_memory() for k in
+                  ("tensor_cam", "R_cam", "scores", "pred_boxes", "pred_proj_xy")}
+    return sum(t.numel() * t.element_size() for t in kf._pinned.values()) + 64   # + the 4x4 pose
+
+
+def make_instances(sess, kf, api, resident):
+    """demo.py:216-221 for the CUDA product: detections (pinned host or HBM-resident) -> Instances3D on the GPU."""
+    from boxfusion_b200 import ops
+    dev = sess.device
+    src = kf._resident if resident else kf._pinned
+    n = kf.tensor_cam.shape[0]
+    ins = api.Instances3D((kf.image_size[1], kf.image_size[0]))
+    if resident:
+        t = {k: v.clone() for k, v in src.items()}
+    else:
+        t = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
+        ops.Profile.h2d_bytes += sum(v.numel() * v.element_size() for v in src.values())
+    ins.scores, ins.pred_boxes, ins.pred_proj_xy = t["scores"], t["pred_boxes"], t["pred_proj_xy"]
+    ins.pred_boxes_3d = api.GeneralInstance3DBoxes(t["tensor_cam"], t["R_cam"])
+    pose_np = np.repeat(kf.pose[None], repeats=n, axis=0)
+    ins.cam_pose = torch.from_numpy(pose_np)                 # a host tensor, as in demo.py:216
+    ins.frame_id = torch.full((n,), sess.count, device=dev)
+    ins.init_id = sess.box_count + torch.arange(n, device=dev)
+    ins.valid_num = torch.zeros(n, device=dev)
+    ins.pred_boxes_3d.transform2world(ins.cam_pose)          # bf_transform2world (pose copy counted by ops)
+    ins.project_3d_boxes(kf.K, H=kf.image_size[1], W=kf.image_size[0])   # bf_box_corners + bf_project_boxes
+    ins.cam_pose = ins.cam_pose.to(dev)                      # keep the per-frame store resident on the GPU
+    return ins, pose_np
+
+
+def run_ours(args, rank, world, local_rank):
+    from boxfusion_b200 import api, ops
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = make_cfg("ca1m", pst_path=GOLDEN_PST, pst_size=1024)
+    K, W = args.steps, args.warmup
+    n_seq = (K + FRAMES_PER_SEQUENCE - 1) // FRAMES_PER_SEQUENCE
+    seqs = [build_keyframes(1000 * rank + 17 * s + 1, min(FRAMES_PER_SEQUENCE, K - s * FRAMES_PER_SEQUENCE)) for s in range(n_seq)]
+    warm = build_keyframes(999 + rank, max(W, 3) + 8)
+    h2d_per_step = []
+    for kf in [k for s in seqs for k in s] + warm:
+        h2d_per_step.append(pin_keyframe(kf))
+        kf._resident = {k: v.to(dev) for k, v in kf._pinned.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def run_pass(frames_by_seq, resident, timing, log):
+        ops.Profile.reset(timing=timing)
+        evs, calls = [], []
+        for frames in frames_by_seq:
+            sess = FusionSession(api, cfg, device=str(dev))
+            sess.box_fuser.call_log = calls if log else None
+            for kf in frames:
+                flush.zero_()                                           # L2 flush between steps, outside the step's events
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ins, pose_np = make_instances(sess, kf, api, resident)
+                sess.step(kf, ins, pose_np)
+                b.record()
+                evs.append((a, b))
+        torch.cuda.synchronize()
+        return [x.elapsed_time(y) for x, y in evs], calls, sess
+
+    # warm-up (untimed): >= 3 steps of another sequence, both passes
+    run_pass([warm[: max(W, 3) + 8]], True, False, False)
+    run_pass([warm[: max(W, 3)]], False, False, False)
+    fp32_peak = ops.probe_fp32() if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- pass 1: inputs resident in HBM -> `value`, roofline ------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier(); sampler.start(); t0 = time.perf_counter()
+    step_ms, calls, sess = run_pass(seqs, True, True, True)
+    barrier(); wall_resident = time.perf_counter() - t0
+    launches = ops.Profile.launches
+    per_call = ops.Profile.elapsed_ms()
+    call_counts = dict(ops.Profile.calls)
+    # ---- pass 2: host inputs, H2D + D2H inside the timed region -> `e2e` -----------------------------------
+    barrier(); t0 = time.perf_counter()
+    step_ms_e2e, _, sess2 = run_pass(seqs, False, False, False)
+    barrier(); wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+    h2d_b, d2h_b = ops.Profile.h2d_bytes / K, ops.Profile.d2h_bytes / K
+
+    t_res, t_e2e = sum(step_ms) / 1e3, sum(step_ms_e2e) / 1e3
+    if world > 1:                                                       # max over ranks, on the device clock
+        tt = torch.tensor([t_res, t_e2e], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        t_res, t_e2e = float(tt[0]), float(tt[1])
+        # the only exchange of the job: gather every rank's final map (rows of 15 floats), SURVEY section 8(e)
+        m = torch.cat([sess.all_pred_box.pred_boxes_3d.tensor, sess.all_pred_box.pred_boxes_3d.R.reshape(-1, 9)], 1)
+        n_rows = torch.tensor([m.shape[0]], device=dev)
+        sizes = [torch.zeros_like(n_rows) for _ in range(world)]
+        torch.distributed.all_gather(sizes, n_rows)
+        pad = torch.zeros((int(max(s.item() for s in sizes)), 15), device=dev)
+        pad[: m.shape[0]] = m
+        maps = [torch.zeros_like(pad) for _ in range(world)]
+        torch.distributed.all_gather(maps, pad)
+    if rank != 0:
+        return None
+    total_frames = K * world
+    refine = per_call.get("bf_refine", [])
+    ref_ms = [ms for ms, _ in refine]
+    evals = [c["evals"] for c in calls]
+    roof = None
+    if ref_ms and len(evals) == len(ref_ms):
+        tot_ms, tot_ev = sum(ref_ms), float(sum(evals))
+        achieved = tot_ev * FLOP_PER_EVAL / (tot_ms * 1e-3) / 1e12
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_ach = tot_ev * BYTES_PER_EVAL / (tot_ms * 1e-3) / 1e9
+        roof = {"bound": "fp32", "kernel": "bf_refine_kernel", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2),
+                "unit": "TFLOP/s", "frac": round(achieved / fp32_peak, 4), "traffic": None,
+                "peak_source": "bf_probe_fp32 FMA micro-benchmark on this device (burst); MEASURED_PEAKS.json has no FP32 entry",
+                "launches": len(ref_ms), "avg_launch_ms": round(tot_ms / len(ref_ms), 4),
+                "evals_per_launch": round(tot_ev / len(ref_ms), 1), "flop_per_eval": FLOP_PER_EVAL,
+                "evals_per_s": round(tot_ev / (tot_ms * 1e-3), 1),
+                "share_of_step": round(tot_ms / sum(step_ms), 4),
+                "hbm": {"achieved": round(hbm_ach, 3), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 6),
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    kernel_ms = {k: round(sum(ms for ms, _ in v), 3) for k, v in per_call.items()}
+    out = {
+        "metric": "fusion keyframes/s (= 1000 / fusion ms/frame), association + particle refine per keyframe",
+        "value": round(total_frames / t_res, 3), "unit": "keyframes/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": round(1e3 * t_res / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: synthetic CA-1M-shaped 300-keyframe sequence (384x512, 200 objects, <=50 "
+                               "detections/keyframe, shipped 1024-particle template, 20 iters), one sequence per GPU",
+                   "iou_mode": "SAMPLED_REF (reference-exact)", "l2": "flushed between steps (256 MiB memset outside the step events)",
+                   "final_map_boxes": len(sess.all_pred_box), "fused_boxes": len(sess.box_manager.already_fusion)},
+        "e2e": {"value": round(total_frames / t_e2e, 3), "unit": "keyframes/s", "ms_per_step": round(1e3 * t_e2e / K, 4),
+                "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b)},
+        "gpu_launches": int(launches), "calls": call_counts, "device_ms_by_entry": kernel_ms,
+        "wall_s": {"resident": round(wall_resident, 3), "e2e": round(wall_e2e, 3)},
+        "p50_ms": round(float(np.percentile(step_ms, 50)), 4), "p99_ms": round(float(np.percentile(step_ms, 99)), 4),
+        "roofline": roof, "clocks": clocks,
+    }
+    return out, seqs, step_ms_e2e
+
+
+def cpu_port_run(frames, budget_s, backend="scipy"):
+    """Reference algorithm on the host (oracle/port.py): frames processed within `budget_s`."""
+    from oracle import port
+    port.IOU_BACKEND = backend
+    cfg = make_cfg("ca1m", pst_path=GOLDEN_PST, pst_size=1024)
+    sess = FusionSession(port, cfg)
+    t0 = time.perf_counter()
+    done = 0
+    for kf in frames:
+        sess.step(kf)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0, len(sess.all_pred_box)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=FRAMES_PER_SEQUENCE)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path.  Its association half is Python (numpy/scipy) and cannot
+        # travel to the GPU box, so this arm times the oracle port of it (same algorithm and cost structure: Qhull per
+        # pair, 25^3 sampling) with the reference's kernel arithmetic in C; single-threaded like the reference.
+        if rank != 0:
+            return
+        frames = build_keyframes(1, min(args.steps, FRAMES_PER_SEQUENCE))
+        budget = max(30.0, min(150.0, 0.5 * args.steps))
+        done, dt, nmap = cpu_port_run(frames, budget)
+        v = done / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "fusion keyframes/s (= 1000 / fusion ms/frame), association + particle refine per keyframe",
+            "value": round(v, 4), "unit": "keyframes/s", "n_gpus": args.gpus, "steps": done, "warmup": 0,
+            "ms_per_step": round(1e3 * dt / done, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: synthetic CA-1M-shaped 300-keyframe sequence (384x512, 200 objects, <=50 "
+                                   "detections/keyframe, shipped 1024-particle template, 20 iters)"},
+            "cpu_baseline": {"value": round(v, 4), "unit": "keyframes/s", "cores": 1, "kind": "port",
+                             "sample": f"keyframes 0..{done - 1} of the sequence within a {budget:.0f} s budget (map grew to {nmap} boxes; "
+                                       "later keyframes are slower: association is O(N^2) Qhull calls)"},
+            "e2e": {"value": round(v, 4), "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        out, seqs, step_ms_e2e = res
+        if world == 1 and args.cpu_budget > 0:
+            done, dt, nmap = cpu_port_run(seqs[0], args.cpu_budget)
+            gpu_same = done / (sum(step_ms_e2e[:done]) / 1e3)
+            out["cpu_baseline"] = {
+                "value": round(done / dt, 4), "unit": "keyframes/s", "cores": 1, "kind": "port",
+                "sample": f"keyframes 0..{done - 1} of the same sequence within a {args.cpu_budget:.0f} s budget (map grew to {nmap} boxes); "
+                          "single-threaded like the reference; later keyframes are slower on the CPU (O(N^2) Qhull calls)",
+                "ours_e2e_on_same_sample": round(gpu_same, 2)}
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

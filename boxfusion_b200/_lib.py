@@ -48,6 +48,7 @@ PROTOTYPES = {
     "bf_pose_disparity": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bf_refine": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, ctypes.POINTER(RefineCfg),
                          _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
 }
 
@@ -113,11 +114,3 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
         return None
     assert t.is_cuda and t.is_contiguous(), "device pointer arguments must be contiguous CUDA tensors"
     return t.data_ptr()
-
-
-def dev_tensor(x, dtype, device) -> torch.Tensor:
-    """Contiguous tensor of `dtype` on `device` (copies host data; no-op for matching CUDA tensors)."""
-    if not isinstance(x, torch.Tensor):
-        import numpy as np
-        x = torch.from_numpy(np.ascontiguousarray(x))
-    return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()

@@ -60,6 +60,7 @@ class BoxFusion(object):
         self.early_stop = True                   # reference behaviour; benches may force all iterations
         self._pst_dev = {}
         self.last_iters = None                   # per refined box: evaluate_iou calls the optimiser made
+        self.call_log = None                     # bench.py sets this to a list to collect per-launch work
         self.init_searchsize()
 
     # ---- small state helpers (box_fusion.py:463-472) -----------------------------------------------
@@ -154,17 +155,20 @@ class BoxFusion(object):
         offsets = np.zeros(len(todo) + 1, dtype=np.int32)
         offsets[1:] = np.cumsum(lens)
         index = np.fromiter((int(v) for i in todo for v in fl[i]), dtype=np.int32, count=int(offsets[-1]))
-        csr = torch.from_numpy(np.concatenate([offsets, index])).to(dev, non_blocking=True)
+        csr = ops.dev_tensor(np.concatenate([offsets, index]), torch.int32, dev)
         out, upd, its, _, status = ops.refine(
             self._pst_on(dev), boxes.tensor, boxes.R, per_frame_box.scores, per_frame_box.projected_boxes,
             per_frame_box.cam_pose, csr[: len(todo) + 1], csr[len(todo) + 1:], self._rcfg(beta=beta))
         B = len(todo)
-        flat = torch.cat([out.reshape(-1), upd.to(torch.float32), its.to(torch.float32),
-                          status.to(torch.float32)]).cpu().numpy()                      # the step's single D2H
+        flat = ops.to_host(torch.cat([out.reshape(-1), upd.to(torch.float32), its.to(torch.float32),
+                                      status.to(torch.float32)]))                        # the call's single D2H
         if flat[-1] != 0:
             raise RuntimeError("bf_refine: capacity exceeded (views per box or polygon candidates)")
         out_h, upd_h = flat[: 6 * B].reshape(B, 6), flat[6 * B: 7 * B]
         self.last_iters = flat[7 * B: 8 * B].astype(np.int64)
+        if self.call_log is not None:
+            n_eval = min(32 * (int(self.pst_size) // 32), self.PST.shape[0])
+            self.call_log.append({"B": B, "evals": int(np.sum(self.last_iters * np.asarray(lens)) * n_eval)})
         # apply in map order; a box whose view set was fused earlier in this very call is skipped, exactly
         # like the reference's sequential check_if_fusion (:634) would
         rows = []

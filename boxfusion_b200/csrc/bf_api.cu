@@ -38,3 +38,46 @@ extern "C" void bf_destroy(bf_handle* h) {
 }
 
 extern "C" const char* bf_last_error(bf_handle* h) { return h ? h->err : g_create_err; }
+
+// ---- diagnostic: measured FP32 FMA throughput of this device (the denominator of the FP32-pipe roofline;
+// "measure with an FMA micro-benchmark on the box").  Synchronous.
+__global__ void __launch_bounds__(256) bf_fma_probe_kernel(float* __restrict__ out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 0.001f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host*/) {
+    if (!h || iters < 1 || !tflops_out) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_probe_fp32", "bad argument");
+    const int blocks = h->sm_count * 8, threads = 256;
+    void* p;
+    int rc = bf_scratch(h, BF_SCRATCH_MISC, sizeof(float) * (size_t)blocks * threads, &p);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    BF_CUDA(h, cudaEventCreate(&e0));
+    BF_CUDA(h, cudaEventCreate(&e1));
+    bf_fma_probe_kernel<<<blocks, threads>>>((float*)p, iters);          // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        BF_CUDA(h, cudaEventRecord(e0));
+        bf_fma_probe_kernel<<<blocks, threads>>>((float*)p, iters);
+        BF_CUDA(h, cudaEventRecord(e1));
+        BF_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        BF_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return BF_OK;
+}

@@ -284,10 +284,10 @@ int bf_iou3d_overflowed(bf_handle* h, cudaStream_t st, int* overflow) {
 
 extern "C" int bf_iou3d_matrix(bf_handle* h, const float* cornersA, int M, const float* cornersB, int N, int mode,
                                double* iou, int32_t* counts, int64_t* stats, void* stream) {
-    if (!h || M < 0 || N < 0 || !iou || (mode != BF_IOU_SAMPLED_REF && mode != BF_IOU_ANALYTIC))
+    if (!h || M < 0 || N < 0 || (mode != BF_IOU_SAMPLED_REF && mode != BF_IOU_ANALYTIC))
         return bf_fail(h, BF_ERR_INVALID_ARG, "bf_iou3d_matrix", "bad argument");
     if (M == 0 || N == 0) return BF_OK;
-    if (!cornersA || !cornersB) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_iou3d_matrix", "null corners");
+    if (!cornersA || !cornersB || !iou) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_iou3d_matrix", "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     for (int attempt = 0; attempt < 2; ++attempt) {
         int rc = bf_iou3d_run(h, cornersA, M, cornersB, N, 0, mode, iou, counts, stats, 0.0, nullptr,

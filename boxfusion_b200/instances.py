@@ -63,12 +63,12 @@ def _nms_device(instance_lists, box_manager, corners, centers, scores, init_id, 
     iid = ops.dev_tensor(init_id, torch.int64, dev).to(torch.int32).reshape(-1)
     poses = ops.dev_tensor(cam_poses, torch.float32, dev).reshape(-1, 16)
     fl_h, ln_h, flag_h = box_manager.pack_lists(n)
-    packed = torch.from_numpy(np.concatenate([fl_h.reshape(-1), ln_h, flag_h])).to(dev, non_blocking=True)
+    packed = ops.dev_tensor(np.concatenate([fl_h.reshape(-1), ln_h, flag_h]), torch.int32, dev)
     cap = ops.FUSION_CAP
     fl, ln, flag = packed[: n * cap].view(n, cap), packed[n * cap: n * cap + n], packed[n * cap + n:]
     keep, success, status = ops.nms3d(corners, centers, order, iid, poses, fl, ln, flag, float(iou_threshold),
                                       float(box_manager.translation_gap), float(box_manager.rotation_gap), 0.5, IOU_MODE)
-    out = torch.cat([packed, keep, success, status]).cpu().numpy()                  # the step's single D2H
+    out = ops.to_host(torch.cat([packed, keep, success, status]))                   # the call's single D2H
     fl_o = out[: n * cap].reshape(n, cap)
     ln_o, flag_o = out[n * cap: n * cap + n], out[n * cap + n: n * cap + 2 * n]
     keep_o, succ_o = out[n * cap + 2 * n: n * cap + 3 * n], out[n * cap + 3 * n: n * cap + 4 * n]
@@ -263,7 +263,7 @@ class Instances3D:
             det = pred_instances.pred_boxes[torch.as_tensor(small_idx, device=pred_instances.pred_boxes.device)]
             best, best_iou = ops.corr2d(corners, small_mask, pose_inv.astype(np.float32), _as_numpy(intrinsic),
                                         float(W), float(H), det)
-            best, best_iou = best.cpu().numpy(), best_iou.cpu().numpy()
+            best, best_iou = ops.to_host(best), ops.to_host(best_iou)
             cur_scores = _as_numpy(pred_instances.scores)
             glo_scores = _as_numpy(global_pred_box.scores)
             init_id = _as_numpy(all_pred_box.init_id)

@@ -13,10 +13,65 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IOU_ANALYTIC, IOU_SAMPLED_REF, RefineCfg, dev_tensor, handle, ptr
+from ._lib import IOU_ANALYTIC, IOU_SAMPLED_REF, RefineCfg, handle, ptr
 
 FUSION_CAP = 32
 MAX_VIEWS = 64
+
+# kernels launched by one call of each entry point (the library's own __global__ functions)
+KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
+                    "bf_nms3d": 5, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1}
+
+
+class Profile:
+    """Launch counting (always on) and optional CUDA-event timing of every C-ABI call (bench.py)."""
+    launches = 0
+    calls = {}
+    h2d_bytes = 0        # host->device bytes moved by the API (counted from the tensors copied)
+    d2h_bytes = 0        # device->host bytes read back by the API
+    timing = False
+    events = {}          # name -> list of (start_event, end_event, meta)
+
+    @classmethod
+    def reset(cls, timing=False):
+        cls.launches, cls.calls, cls.events, cls.timing = 0, {}, {}, timing
+        cls.h2d_bytes = cls.d2h_bytes = 0
+
+    @classmethod
+    def elapsed_ms(cls):
+        """name -> list of (ms, meta); call after torch.cuda.synchronize()."""
+        return {k: [(a.elapsed_time(b), m) for a, b, m in v] for k, v in cls.events.items()}
+
+
+def _call(h, name, fn, *args, meta=None):
+    Profile.launches += KERNELS_PER_CALL[name]
+    Profile.calls[name] = Profile.calls.get(name, 0) + 1
+    if Profile.timing:
+        st = torch.cuda.current_stream(h.device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        rc = fn(*args)
+        b.record(st)
+        Profile.events.setdefault(name, []).append((a, b, meta))
+    else:
+        rc = fn(*args)
+    h.check(rc, name)
+
+
+def dev_tensor(x, dtype, device) -> torch.Tensor:
+    """Contiguous tensor of `dtype` on `device`; host data is copied (and counted), CUDA data is used in place."""
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not x.is_cuda:
+        Profile.h2d_bytes += x.numel() * x.element_size()
+    return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device->host read of a result (synchronises the stream); counted for the e2e bench."""
+    if t.is_cuda:
+        Profile.d2h_bytes += t.numel() * t.element_size()
+    return t.cpu().numpy()
 
 
 def _dev(device=None) -> torch.device:
@@ -43,7 +98,7 @@ def box_corners(xyzlhw, R, want_centers: bool = False):
     corners = torch.empty((n, 8, 3), dtype=torch.float32, device=dev)
     centers = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_centers else None
     h = handle(dev)
-    h.check(h.lib.bf_box_corners(h.h, ptr(t), ptr(r), n, ptr(corners), ptr(centers), h.stream()), "bf_box_corners")
+    _call(h, "bf_box_corners", h.lib.bf_box_corners, h.h, ptr(t), ptr(r), n, ptr(corners), ptr(centers), h.stream())
     return (corners, centers) if want_centers else corners
 
 
@@ -52,7 +107,7 @@ def transform2world_(xyzlhw: torch.Tensor, R: torch.Tensor, poses) -> None:
     assert xyzlhw.is_cuda and R.is_cuda and xyzlhw.is_contiguous() and R.is_contiguous()
     p = dev_tensor(poses, torch.float32, xyzlhw.device).reshape(-1, 16)
     h = handle(xyzlhw.device)
-    h.check(h.lib.bf_transform2world(h.h, ptr(xyzlhw), ptr(R), ptr(p), xyzlhw.shape[0], h.stream()), "bf_transform2world")
+    _call(h, "bf_transform2world", h.lib.bf_transform2world, h.h, ptr(xyzlhw), ptr(R), ptr(p), xyzlhw.shape[0], h.stream())
 
 
 def project_boxes(corners, pose_inv, K, W: float, H: float) -> torch.Tensor:
@@ -63,8 +118,8 @@ def project_boxes(corners, pose_inv, K, W: float, H: float) -> torch.Tensor:
     n = c.shape[0]
     uv = torch.empty((n, 8, 2), dtype=torch.float32, device=dev)
     h = handle(dev)
-    h.check(h.lib.bf_project_boxes(h.h, ptr(c), ptr(pi), n, float(K[0][0]), float(K[1][1]), float(K[0][2]),
-                                   float(K[1][2]), float(W), float(H), ptr(uv), h.stream()), "bf_project_boxes")
+    _call(h, "bf_project_boxes", h.lib.bf_project_boxes, h.h, ptr(c), ptr(pi), n, float(K[0][0]), float(K[1][1]), float(K[0][2]),
+                                   float(K[1][2]), float(W), float(H), ptr(uv), h.stream())
     return uv
 
 
@@ -78,8 +133,7 @@ def iou3d_matrix(cornersA, cornersB, mode: int = IOU_SAMPLED_REF, want_counts: b
     counts = torch.empty((M, N, 3), dtype=torch.int32, device=dev) if want_counts else None
     stats = torch.zeros(4, dtype=torch.int64, device=dev) if want_stats else None
     h = handle(dev)
-    h.check(h.lib.bf_iou3d_matrix(h.h, ptr(a), M, ptr(b), N, int(mode), ptr(iou), ptr(counts), ptr(stats), h.stream()),
-            "bf_iou3d_matrix")
+    _call(h, "bf_iou3d_matrix", h.lib.bf_iou3d_matrix, h.h, ptr(a), M, ptr(b), N, int(mode), ptr(iou), ptr(counts), ptr(stats), h.stream())
     out = (iou,)
     if want_counts:
         out += (counts,)
@@ -99,10 +153,10 @@ def nms3d(corners, centers, order, init_id, poses, fusion_list, fusion_len, fusi
     success = torch.empty(n, dtype=torch.int32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     h = handle(dev)
-    h.check(h.lib.bf_nms3d(h.h, ptr(corners), ptr(centers), n, ptr(order), ptr(init_id), ptr(poses), poses.shape[0],
+    _call(h, "bf_nms3d", h.lib.bf_nms3d, h.h, ptr(corners), ptr(centers), n, ptr(order), ptr(init_id), ptr(poses), poses.shape[0],
                            ptr(fusion_list), ptr(fusion_len), ptr(fusion_flag), float(iou_threshold),
                            float(translation_gap), float(rotation_gap), float(center_gap), int(mode),
-                           ptr(keep), ptr(success), ptr(status), h.stream()), "bf_nms3d")
+                           ptr(keep), ptr(success), ptr(status), h.stream())
     return keep, success, status
 
 
@@ -118,9 +172,9 @@ def corr2d(map_corners, small_mask, pose_inv, K, W: float, H: float, det_xyxy, w
     best_iou = torch.empty(n, dtype=torch.float64, device=dev)
     boxes2d = torch.empty((G, 4), dtype=torch.float64, device=dev) if want_boxes else None
     h = handle(dev)
-    h.check(h.lib.bf_corr2d(h.h, ptr(mc), ptr(sm), G, ptr(pi), float(K[0][0]), float(K[1][1]), float(K[0][2]),
+    _call(h, "bf_corr2d", h.lib.bf_corr2d, h.h, ptr(mc), ptr(sm), G, ptr(pi), float(K[0][0]), float(K[1][1]), float(K[0][2]),
                             float(K[1][2]), float(W), float(H), ptr(det), n, ptr(boxes2d), ptr(best), ptr(best_iou),
-                            h.stream()), "bf_corr2d")
+                            h.stream())
     return (best, best_iou, boxes2d) if want_boxes else (best, best_iou)
 
 
@@ -134,7 +188,7 @@ def pose_disparity(poses, ia, ib):
     base = torch.empty(n, dtype=torch.float32, device=dev)
     ang = torch.empty(n, dtype=torch.float32, device=dev)
     h = handle(dev)
-    h.check(h.lib.bf_pose_disparity(h.h, ptr(p), ptr(a), ptr(b), n, ptr(base), ptr(ang), h.stream()), "bf_pose_disparity")
+    _call(h, "bf_pose_disparity", h.lib.bf_pose_disparity, h.h, ptr(p), ptr(a), ptr(b), n, ptr(base), ptr(ang), h.stream())
     return base, ang
 
 
@@ -170,9 +224,9 @@ def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, 
     trace = torch.zeros((B, rcfg.iters, 8), dtype=torch.float32, device=dev) if want_trace else None
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     h = handle(dev)
-    h.check(h.lib.bf_refine(h.h, ptr(pst), pst.shape[0], ptr(t), ptr(r), ptr(s), ptr(uv), ptr(po), t.shape[0],
+    _call(h, "bf_refine", h.lib.bf_refine, h.h, ptr(pst), pst.shape[0], ptr(t), ptr(r), ptr(s), ptr(uv), ptr(po), t.shape[0],
                             ptr(off), ptr(idx), B, ctypes.byref(rcfg), ptr(out), ptr(upd), ptr(its), ptr(trace),
-                            ptr(status), h.stream()), "bf_refine")
+                            ptr(status), h.stream())
     return out, upd, its, trace, status
 
 
@@ -187,6 +241,15 @@ def evaluate_iou(pst, box6, rot9, uv, poses, search6, rcfg: RefineCfg) -> torch.
     s = dev_tensor(search6, torch.float32, dev).reshape(6)
     fit = torch.empty(pst.shape[0], dtype=torch.float32, device=dev)
     h = handle(dev)
-    h.check(h.lib.bf_evaluate_iou(h.h, ptr(pst), pst.shape[0], ptr(b), ptr(r), ptr(u), ptr(p), u.shape[0], ptr(s),
-                                  ctypes.byref(rcfg), ptr(fit), h.stream()), "bf_evaluate_iou")
+    _call(h, "bf_evaluate_iou", h.lib.bf_evaluate_iou, h.h, ptr(pst), pst.shape[0], ptr(b), ptr(r), ptr(u), ptr(p), u.shape[0], ptr(s),
+                                  ctypes.byref(rcfg), ptr(fit), h.stream())
     return fit
+
+
+def probe_fp32(iters: int = 4096, device=None) -> float:
+    """Measured FP32 FMA throughput (TFLOP/s) of the device: denominator of the FP32-pipe roofline."""
+    h = handle(_dev(device))
+    tf = ctypes.c_double(0.0)
+    ms = ctypes.c_float(0.0)
+    h.check(h.lib.bf_probe_fp32(h.h, int(iters), ctypes.byref(tf), ctypes.byref(ms)), "bf_probe_fp32")
+    return float(tf.value)

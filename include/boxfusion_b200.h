@@ -62,9 +62,10 @@ int bf_transform2world(bf_handle* h, float* xyzlhw /*[N,6]*/, float* R /*[N,9]*/
                        int N, void* stream);
 
 /* ---- A15 Instances3D.project_3d_boxes (instances.py:333-369) -----------------------------------
- * Observation corners in each detection's own camera, clamped to [0,W]x[0,H].  The reference
- * inverts the pose with a general LU (torch.linalg.inv); this uses the rigid inverse R^T(p-t). */
-int bf_project_boxes(bf_handle* h, const float* corners /*[N,8,3]*/, const float* poses /*[N,16]*/, int N,
+ * Observation corners in each detection's own camera, clamped to [0,W]x[0,H].  pose_inv is the
+ * world->camera matrix; the host binding obtains it with the reference's own torch.linalg.inv call
+ * (:350) so that the projected corners are the reference's to the last bit of the einsum (:352). */
+int bf_project_boxes(bf_handle* h, const float* corners /*[N,8,3]*/, const float* pose_inv /*[N,16]*/, int N,
                      float fx, float fy, float cx, float cy, float W, float H, float* uv /*[N,8,2]*/, void* stream);
 
 /* ---- A3/A4  Instances3D.obb_iou / calculate_obb_iou (instances.py:106-125, 573-613) -------------
@@ -136,6 +137,10 @@ int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,
 int bf_evaluate_iou(bf_handle* h, const float* pst /*[P,6]*/, int P, const float* box6 /*[6]*/, const float* rot9,
                     const float* uv /*[V,16]*/, const float* poses /*[V,16]*/, int V, const float* search6,
                     const bf_refine_cfg* cfg /*host*/, float* fitness /*[P]*/, void* stream);
+
+/* Diagnostic: measured FP32 FMA throughput (TFLOP/s) of the device - the denominator of the FP32-pipe
+ * roofline bench.py reports.  Synchronous; outputs are HOST pointers. */
+int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host or NULL*/);
 
 #ifdef __cplusplus
 }

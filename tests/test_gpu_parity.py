@@ -103,10 +103,11 @@ def test_analytic_iou_matches_fp64_oracle():
     ref = analytic_oracle.iou_matrix(ca, cb)
     np.testing.assert_allclose(iou, ref, rtol=1e-9, atol=1e-12)
     assert (ref > 0.1).sum() > 40 and stats[3] == stats[1]               # every AABB-passing pair was co-axial
-    # sampled estimator agrees with the analytic value to its discretisation error (<= 0.036 abs)
+    # the reference's sampled estimator agrees with the analytic value only to its 25^3 discretisation error
+    # (SURVEY F2 measured <= 0.036 abs on 300 pairs; thin boxes reach ~0.07 here)
     samp = ops.iou3d_matrix(ca, cb).cpu().numpy()
     both = (ref > 0) & (samp > 0)
-    assert np.abs(ref - samp)[both].max() < 0.06
+    assert np.abs(ref - samp)[both].max() < 0.1 and np.median(np.abs(ref - samp)[both]) < 0.01
 
 
 def test_analytic_falls_back_to_sampled_for_tilted_boxes():
@@ -131,8 +132,8 @@ def _nms_case(n_map, n_det, seed, tilt=0.01):
         k = 1 if i >= n_map else int(rs.choice([1, 1, 2, 3, 4]))
         lists.append(list(range(M, M + k))); M += k
     poses = np.tile(np.eye(4, dtype=np.float32), (M, 1, 1))
-    from scipy.spatial.transform import Rotation as Rot
-    poses[:, :3, :3] = Rot.from_euler("z", rs.uniform(0, 90, M), degrees=True).as_matrix().astype(np.float32)
+    ang = np.deg2rad(rs.uniform(0, 90, M))
+    poses[:, 0, 0], poses[:, 0, 1], poses[:, 1, 0], poses[:, 1, 1] = np.cos(ang), -np.sin(ang), np.sin(ang), np.cos(ang)
     poses[:, :3, 3] = rs.uniform(-1.5, 1.5, (M, 3)).astype(np.float32)
     init_id = np.array([l[0] for l in lists], dtype=np.int64)
     flags = [int(rs.rand() < 0.2) if len(l) > 1 else 0 for l in lists]
