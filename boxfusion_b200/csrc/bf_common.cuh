@@ -28,6 +28,7 @@ struct bf_handle {
     char err[512];
     void* buf[BF_SCRATCH_SLOTS];
     size_t cap[BF_SCRATCH_SLOTS];
+    int last_refine_cluster;    // cluster size the last bf_refine launch used (diagnostic)
 };
 
 static inline int bf_fail(bf_handle* h, int code, const char* what, const char* detail) {
@@ -55,7 +56,7 @@ static inline int bf_scratch(bf_handle* h, int slot, size_t bytes, void** out) {
         if (h->buf[slot]) BF_CUDA(h, cudaFree(h->buf[slot]));
         h->buf[slot] = nullptr;
         h->cap[slot] = 0;
-        size_t want = bytes + bytes / 2 + 4096;
+        size_t want = 2 * bytes + 65536;                 // geometric growth: a growing map reallocates O(log N) times
         BF_CUDA(h, cudaMalloc(&h->buf[slot], want));
         h->cap[slot] = want;
     }

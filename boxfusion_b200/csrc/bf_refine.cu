@@ -14,11 +14,13 @@
 // bit-identical to the oracle - not merely within tolerance.  Doubles appear exactly where the
 // reference uses them (line_intersection, the 0.00001 literal, the float64 box state).
 #include "bf_common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 struct P2 { float x, y; };
 
 #define BF_CAND_MAX 48          // reference buffer: 36 (box_fusion.py:378); overflow is reported, not UB
-#define BF_REFINE_THREADS 512
+#define BF_REFINE_THREADS 256
 
 __device__ __forceinline__ float bf_cross(const P2 o, const P2 a, const P2 b) {          // :74-76
     return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
@@ -193,66 +195,64 @@ struct bf_refine_params {
     float* out_xyzlhw; int32_t* out_updated; int32_t* out_iters; float* trace; int32_t* status;
 };
 
-struct bf_refine_state {     // shared, written by thread 0 between phases
+struct bf_refine_state {     // optimiser state of one box; the cluster leader's copy is authoritative
     double g[6];
     float box6[6];
     float rot[9];
     float search[6], prev[6];
-    float mt[6];
-    float min_iou;
-    int success, previous_success, fail, need_update, done;
-    int hits;
+    int previous_success, fail, need_update, done;
     float acc[8];
 };
 
-// Evaluate fitness[P] for the current state (evaluate_iou, :413-461).  All threads of the CTA.
-__device__ __forceinline__ void bf_fitness_pass(const bf_refine_params& prm, const bf_refine_state& S, const bf_view* views,
-                                                int V, int n_eval, float* fit, int* overflow) {
-    const bf_refine_cfg& cfg = prm.cfg;
-    for (int p = threadIdx.x; p < prm.P; p += blockDim.x) {
-        float value = 0.0f, count = 0.0f;
-        if (p < n_eval) {
-            float pst6[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
-            float c[8][3];
-            bf_particle_corners(S.box6, pst6, S.search, S.rot, c);
-            for (int v = 0; v < V; ++v) {               // ascending views: the host order of the atomicAdd sum (:400)
-                value += bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, overflow);
-                count += 1;
-            }
-        }
-        fit[p] = value / (count + 1e-6f);               // :454
-    }
-}
+// ---- shared-memory layout (identical in every CTA of a cluster so that DSMEM offsets match) ------------
+struct bf_refine_smem {
+    bf_refine_state S;
+    bf_view views[BF_MAX_VIEWS];
+    int warp_cnt[32];
+    float vbox[6 * BF_MAX_VIEWS];        // gathered view boxes (init_opt_params)
+    float vscore[BF_MAX_VIEWS];
+    float col[3 * BF_MAX_VIEWS];
+    int overflow;
+    // followed by: float fit[P]; int sel[max_hits]; float contrib[pair_cap]
+};
 
-extern __shared__ unsigned char bf_refine_smem[];
+extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
 
-__global__ void __launch_bounds__(BF_REFINE_THREADS)
-bf_refine_kernel(const bf_refine_params prm) {
-    const int b = blockIdx.x;
+// One thread-block CLUSTER per map box.  Work items of an optimiser iteration are spread over all CTAs of
+// the cluster; every CTA writes its results straight into the leader's shared memory (DSMEM), the leader
+// reduces in the reference's order and publishes the new state, two cluster barriers per iteration.
+//   pair mode     (n_eval*V <= pair_cap): one work item = one (particle, view); contributions are stored
+//                 view-major and summed per particle in ascending view order by the leader
+//   particle mode (larger problems): one work item = one particle, views summed sequentially in registers
+__global__ void __launch_bounds__(BF_REFINE_THREADS, 2)
+bf_refine_kernel(const bf_refine_params prm, int pair_cap) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned C = cluster.num_blocks();
+    const unsigned crank = cluster.block_rank();
+    const int b = blockIdx.x / C;
     const int tid = threadIdx.x;
+    const int T = blockDim.x;
     const int v0 = prm.view_offsets[b];
     const int V = prm.view_offsets[b + 1] - v0;
     const bf_refine_cfg& cfg = prm.cfg;
-    // shared layout
-    bf_refine_state* S = (bf_refine_state*)bf_refine_smem;
-    bf_view* views = (bf_view*)(S + 1);
-    float* fit = (float*)(views + BF_MAX_VIEWS);
+    bf_refine_smem* sm = (bf_refine_smem*)bf_refine_smem_raw;
+    bf_refine_state* S = &sm->S;
+    bf_view* views = sm->views;
+    float* fit = (float*)(sm + 1);
     int* sel = (int*)(fit + prm.P);
-    int* warp_cnt = sel + cfg.max_hits;                  // [32]
-    float* vbox = (float*)(warp_cnt + 32);               // [V,6] gathered view boxes (init_opt_params)
-    float* vscore = vbox + 6 * BF_MAX_VIEWS;             // [V]
-    float* col = vscore + BF_MAX_VIEWS;                  // [3,V]
-    __shared__ int s_overflow;
-    if (tid == 0) s_overflow = 0;
-    if (V < 1 || V > BF_MAX_VIEWS) {                     // flagged in status by bf_check_views_kernel2
-        if (tid == 0) { prm.out_updated[b] = 0; prm.out_iters[b] = 0; }
+    float* contrib = (float*)(sel + cfg.max_hits);
+    if (tid == 0) sm->overflow = 0;
+    if (V < 1 || V > BF_MAX_VIEWS) {                     // flagged in status by bf_check_views_kernel2 (cluster-uniform)
+        if (tid == 0 && crank == 0) { prm.out_updated[b] = 0; prm.out_iters[b] = 0; }
         return;
     }
+    // leader's buffers as seen from this CTA
+    float* l_fit = cluster.map_shared_rank(fit, 0);
+    float* l_contrib = cluster.map_shared_rank(contrib, 0);
+    const bf_refine_state* l_S = cluster.map_shared_rank(S, 0);
 
-    // ---- stage the views: pose rows, observation hull (:367,375) and its area (:389) --------------
-    for (int v = tid; v < V; v += blockDim.x) {
+    // ---- stage the views in every CTA: pose rows, observation hull (:367,375) and its area (:389) -------
+    for (int v = tid; v < V; v += T) {
         const int m = prm.view_index[v0 + v];
         bf_view& vw = views[v];
 #pragma unroll
@@ -265,13 +265,14 @@ bf_refine_kernel(const bf_refine_params prm) {
         for (int k = 0; k < 8; ++k) vw.hull[k] = ht[k < vw.nt ? k : 0];
         vw.area_t = bf_shoelace(ht, vw.nt);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) vbox[6 * v + k] = prm.per_xyzlhw[6 * (size_t)m + k];
-        vscore[v] = prm.per_scores[m];
+        for (int k = 0; k < 6; ++k) sm->vbox[6 * v + k] = prm.per_xyzlhw[6 * (size_t)m + k];
+        sm->vscore[v] = prm.per_scores[m];
     }
     __syncthreads();
 
-    // ---- init_opt_params (:566-600) + init_searchsize (:468-472), thread 0 -------------------------
+    // ---- init_opt_params (:566-600) + init_searchsize (:468-472): thread 0 of every CTA (same result) ----
     if (tid == 0) {
+        const float* vbox = sm->vbox; const float* vscore = sm->vscore; float* col = sm->col;
         int best = 0;
         for (int v = 1; v < V; ++v) if (vscore[v] > vscore[best]) best = v;
         for (int k = 0; k < 3; ++k) {
@@ -298,98 +299,146 @@ bf_refine_kernel(const bf_refine_params prm) {
     __syncthreads();
 
     const int n_eval = min(32 * (cfg.pst_size / 32), prm.P);
+    const bool pair_mode = (long long)n_eval * V <= (long long)pair_cap;
     const float beta = (float)cfg.beta, omb = (float)(1.0 - cfg.beta);
     int overflow = 0;
     int it = 0;
+    cluster.sync();                                      // every CTA's shared memory is initialised
     for (int n = 0; n < cfg.iters; ++n) {
-        bf_fitness_pass(prm, *S, views, V, n_eval, fit, &overflow);
+        // ---- evaluate_iou (:413-461) spread over the cluster ------------------------------------------------
+        if (pair_mode) {
+            const int items = n_eval * V;
+            for (int w = crank * T + tid; w < items; w += C * T) {
+                const int v = w / n_eval, p = w - v * n_eval;          // view-major: a warp works on one view
+                float pst6[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
+                float c[8][3];
+                bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
+                l_contrib[w] = bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
+            }
+        } else {
+            for (int p = crank * T + tid; p < n_eval; p += C * T) {
+                float pst6[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
+                float c[8][3];
+                bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
+                float value = 0.0f, count = 0.0f;
+                for (int v = 0; v < V; ++v) {           // ascending views: the host order of the atomicAdd sum (:400)
+                    value += bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
+                    count += 1;
+                }
+                l_fit[p] = value / (count + 1e-6f);     // :454
+            }
+        }
         ++it;
-        __syncthreads();
-        // ---- cal_transform (:475-535): first `max_hits` particles j >= 1 with fit[j] < fit[0], index order
-        const float origin = fit[0];
-        int total = 0;
-        for (int base = 0; base < prm.P && total < cfg.max_hits; base += blockDim.x) {
-            const int j = base + tid;
-            const bool hit = (j >= 1 && j < prm.P) && (fit[j] < origin);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            const int lane = tid & 31, warp = tid >> 5;
-            if (lane == 0) warp_cnt[warp] = __popc(bal);
+        cluster.sync();
+        if (crank == 0) {
+            // ---- fitness per particle, views summed in ascending order (:400-401, :454) ---------------------
+            if (pair_mode) {
+                for (int p = tid; p < n_eval; p += T) {
+                    float value = 0.0f, count = 0.0f;
+                    for (int v = 0; v < V; ++v) { value += contrib[v * n_eval + p]; count += 1; }
+                    fit[p] = value / (count + 1e-6f);
+                }
+            }
+            for (int p = n_eval + tid; p < prm.P; p += T) fit[p] = 0.0f / (0.0f + 1e-6f);   // never launched
             __syncthreads();
-            int before = total, all = 0;
-            const int nw = blockDim.x >> 5;
-            for (int w = 0; w < nw; ++w) { const int cw = warp_cnt[w]; if (w < warp) before += cw; all += cw; }
-            const int pos = before + __popc(bal & ((1u << lane) - 1u));
-            if (hit && pos < cfg.max_hits) sel[pos] = j;
-            total += all;
+            // ---- cal_transform (:475-535): first `max_hits` particles j >= 1 with fit[j] < fit[0], index order
+            const float origin = fit[0];
+            int total = 0;
+            for (int base = 0; base < prm.P && total < cfg.max_hits; base += T) {
+                const int j = base + tid;
+                const bool hit = (j >= 1 && j < prm.P) && (fit[j] < origin);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                const int lane = tid & 31, warp = tid >> 5;
+                if (lane == 0) sm->warp_cnt[warp] = __popc(bal);
+                __syncthreads();
+                int before = total, all = 0;
+                const int nw = T >> 5;
+                for (int w = 0; w < nw; ++w) { const int cw = sm->warp_cnt[w]; if (w < warp) before += cw; all += cw; }
+                const int pos = before + __popc(bal & ((1u << lane) - 1u));
+                if (hit && pos < cfg.max_hits) sel[pos] = j;
+                total += all;
+                __syncthreads();
+            }
+            const int hits = min(total, cfg.max_hits);
+            // sequential float32 accumulation in index order: 6 PST sums, weight sum, weighted-fitness sum
+            if (tid < 8) {
+                float acc = 0.0f;
+                for (int q = 0; q < hits; ++q) {
+                    const int j = sel[q];
+                    const float w = origin - fit[j];
+                    const float term = (tid < 6) ? __ldg(prm.pst + 6 * (size_t)j + tid) * w : ((tid == 6) ? w : fit[j] * w);
+                    acc += term;
+                }
+                S->acc[tid] = acc;
+            }
             __syncthreads();
+            if (tid == 0) {
+                int success;
+                float min_iou, mt[6] = {0, 0, 0, 0, 0, 0};
+                if (hits <= 0) { success = 0; min_iou = origin; }
+                else {
+                    success = 1;
+                    const float sw = S->acc[6];
+                    min_iou = S->acc[7] / sw;
+                    for (int k = 0; k < 6; ++k) mt[k] = (S->acc[k] / sw) * S->search[k];
+                }
+                // update_PST (:537-562)
+                const float ms = 1e-3f;
+                float s[6];
+                for (int k = 0; k < 6; ++k) s[k] = fabsf(mt[k]) + ms;
+                float n2 = s[0] * s[0];
+                for (int k = 1; k < 6; ++k) n2 = n2 + s[k] * s[k];
+                const float nrm = sqrtf(n2);
+                for (int k = 3; k < 6; ++k) S->search[k] = cfg.shape_scale * min_iou * (s[k] / nrm) + ms;
+                for (int k = 0; k < 3; ++k) S->search[k] = cfg.center_scale * min_iou * (s[k] / nrm) + ms;
+                if (S->previous_success && success)                                                  // :685-691
+                    for (int k = 0; k < 6; ++k) S->search[k] = beta * S->search[k] + omb * S->prev[k];
+                if (success) {                                                                        // :694-706
+                    S->need_update = 1; S->previous_success = 1; S->fail = 0;
+                    for (int k = 0; k < 6; ++k) { S->g[k] += (double)mt[k]; S->prev[k] = S->search[k]; }
+                } else { S->fail += 1; S->previous_success = 0; }
+                if (prm.trace) {
+                    float* tr = prm.trace + ((size_t)b * cfg.iters + n) * 8;
+                    tr[0] = (float)success; tr[1] = min_iou;
+                    for (int k = 0; k < 6; ++k) tr[2 + k] = S->search[k];
+                }
+                for (int k = 0; k < 6; ++k) S->box6[k] = (float)S->g[k];
+                S->done = (cfg.early_stop && S->fail >= 3) ? 1 : 0;                                   // :713
+            }
         }
-        const int hits = min(total, cfg.max_hits);
-        // sequential float32 accumulation in index order: 6 PST sums, weight sum, weighted-fitness sum
-        if (tid < 8) {
-            float acc = 0.0f;
-            for (int q = 0; q < hits; ++q) {
-                const int j = sel[q];
-                const float w = origin - fit[j];
-                const float term = (tid < 6) ? __ldg(prm.pst + 6 * (size_t)j + tid) * w : ((tid == 6) ? w : fit[j] * w);
-                acc += term;
-            }
-            S->acc[tid] = acc;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int success;
-            float min_iou, mt[6] = {0, 0, 0, 0, 0, 0};
-            if (hits <= 0) { success = 0; min_iou = origin; }
-            else {
-                success = 1;
-                const float sw = S->acc[6];
-                min_iou = S->acc[7] / sw;
-                for (int k = 0; k < 6; ++k) mt[k] = (S->acc[k] / sw) * S->search[k];
-            }
-            // update_PST (:537-562)
-            const float ms = 1e-3f;
-            float s[6];
-            for (int k = 0; k < 6; ++k) s[k] = fabsf(mt[k]) + ms;
-            float n2 = s[0] * s[0];
-            for (int k = 1; k < 6; ++k) n2 = n2 + s[k] * s[k];
-            const float nrm = sqrtf(n2);
-            for (int k = 3; k < 6; ++k) S->search[k] = cfg.shape_scale * min_iou * (s[k] / nrm) + ms;
-            for (int k = 0; k < 3; ++k) S->search[k] = cfg.center_scale * min_iou * (s[k] / nrm) + ms;
-            if (S->previous_success && success)                                                  // :685-691
-                for (int k = 0; k < 6; ++k) S->search[k] = beta * S->search[k] + omb * S->prev[k];
-            if (success) {                                                                        // :694-706
-                S->need_update = 1; S->previous_success = 1; S->fail = 0;
-                for (int k = 0; k < 6; ++k) { S->g[k] += (double)mt[k]; S->prev[k] = S->search[k]; }
-            } else { S->fail += 1; S->previous_success = 0; }
-            if (prm.trace) {
-                float* tr = prm.trace + ((size_t)b * cfg.iters + n) * 8;
-                tr[0] = (float)success; tr[1] = min_iou;
-                for (int k = 0; k < 6; ++k) tr[2 + k] = S->search[k];
-            }
-            for (int k = 0; k < 6; ++k) S->box6[k] = (float)S->g[k];
-            S->done = (cfg.early_stop && S->fail >= 3) ? 1 : 0;                                   // :713
+        cluster.sync();                                  // leader state published
+        if (crank != 0) {
+            if (tid < 6) { S->box6[tid] = l_S->box6[tid]; S->search[tid] = l_S->search[tid]; }
+            if (tid == 6) S->done = l_S->done;
         }
         __syncthreads();
         if (S->done) break;
     }
-    if (overflow) atomicExch(&s_overflow, 1);
-    __syncthreads();
+    if (overflow) atomicExch(&sm->overflow, 1);
+    cluster.sync();                                      // nobody reads the leader's shared memory after this
     if (tid == 0) {
-        prm.out_iters[b] = it;
-        prm.out_updated[b] = S->need_update;
-        if (S->need_update) {                                                                     // :716-721
-            for (int k = 3; k < 6; ++k) if (S->g[k] < 0.01) S->g[k] = 0.01;
-            for (int k = 0; k < 6; ++k) prm.out_xyzlhw[6 * (size_t)b + k] = (float)S->g[k];
-        } else {
-            for (int k = 0; k < 6; ++k) prm.out_xyzlhw[6 * (size_t)b + k] = 0.0f;
+        if (sm->overflow) atomicExch(prm.status, BF_ERR_CAPACITY);
+        if (crank == 0) {
+            prm.out_iters[b] = it;
+            prm.out_updated[b] = S->need_update;
+            if (S->need_update) {                                                                     // :716-721
+                for (int k = 3; k < 6; ++k) if (S->g[k] < 0.01) S->g[k] = 0.01;
+                for (int k = 0; k < 6; ++k) prm.out_xyzlhw[6 * (size_t)b + k] = (float)S->g[k];
+            } else {
+                for (int k = 0; k < 6; ++k) prm.out_xyzlhw[6 * (size_t)b + k] = 0.0f;
+            }
         }
-        if (s_overflow) atomicExch(prm.status, BF_ERR_CAPACITY);
     }
 }
 
-static size_t bf_refine_smem_bytes(int P, int max_hits) {
-    return sizeof(bf_refine_state) + sizeof(bf_view) * BF_MAX_VIEWS + sizeof(float) * (size_t)P + sizeof(int) * (size_t)max_hits +
-           sizeof(int) * 32 + sizeof(float) * (6 * BF_MAX_VIEWS + BF_MAX_VIEWS + 3 * BF_MAX_VIEWS) + 64;
+#define BF_PAIR_CAP 16384      // (particle, view) contributions the leader can hold: 64 KB
+
+static size_t bf_refine_smem_bytes(int P, int max_hits, int pair_cap) {
+    return sizeof(bf_refine_smem) + sizeof(float) * (size_t)P + sizeof(int) * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + 16;
 }
 
 __global__ void bf_check_views_kernel(const int32_t* __restrict__ off, int B, int32_t* __restrict__ status) {
@@ -421,10 +470,35 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
     prm.per_uv = per_uv; prm.per_poses = per_poses; prm.view_offsets = view_offsets; prm.view_index = view_index;
     prm.B = B; prm.cfg = *cfg; prm.out_xyzlhw = out_xyzlhw; prm.out_updated = out_updated; prm.out_iters = out_iters;
     prm.trace = trace; prm.status = status;
-    const size_t smem = bf_refine_smem_bytes(P, cfg->max_hits);
+    const int pair_cap = BF_PAIR_CAP;
+    const size_t smem = bf_refine_smem_bytes(P, cfg->max_hits, pair_cap);
     BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bf_refine_kernel<<<B, BF_REFINE_THREADS, smem, st>>>(prm);
-    BF_LAUNCH_CHECK(h, "bf_refine_kernel");
+    BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // cluster size: enough CTAs that a box's work items are ~2 per thread, as long as the whole launch still
+    // fits the machine about twice over (2 CTAs of 256 threads per SM)
+    const int n_eval = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
+    const long long hint_items = (long long)n_eval * (cfg->views_hint > 0 ? cfg->views_hint : 8);
+    int C = 1;
+    while (C < 16 && (long long)C * BF_REFINE_THREADS * 2 < hint_items) C *= 2;
+    while (C > 1 && (long long)B * C > 4LL * h->sm_count) C /= 2;
+    for (;; C /= 2) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)(B * C)); lc.blockDim = dim3(BF_REFINE_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, bf_refine_kernel, &lc);
+        if ((e != cudaSuccess || nclusters < 1) && C > 1) { cudaGetLastError(); continue; }
+        e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap);
+        if (e != cudaSuccess) {
+            if (C > 1) { cudaGetLastError(); continue; }
+            return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
+        }
+        h->last_refine_cluster = C;
+        break;
+    }
     return BF_OK;
 }
 

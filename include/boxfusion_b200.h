@@ -123,6 +123,7 @@ typedef struct {
     float fx, cx, fy, cy;     /* K[0],K[2],K[5],K[6] of the flattened 4x4 (box_fusion.py:356-357) */
     int32_t max_hits;         /* 200                                                     */
     int32_t early_stop;       /* 1: stop after 3 consecutive failures (reference); 0: run all iters */
+    int32_t views_hint;       /* typical views per box of this call (0 = unknown): sizes the thread-block cluster */
 } bf_refine_cfg;
 
 int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,
