@@ -28,7 +28,7 @@ class RefineCfg(ctypes.Structure):
                 ("center_init", _f32), ("shape_init", _f32), ("center_scale", _f32), ("shape_scale", _f32),
                 ("beta", _f64), ("img_h", _f32), ("img_w", _f32),
                 ("fx", _f32), ("cx", _f32), ("fy", _f32), ("cy", _f32),
-                ("max_hits", ctypes.c_int32), ("early_stop", ctypes.c_int32), ("views_hint", ctypes.c_int32)]
+                ("max_hits", ctypes.c_int32), ("early_stop", ctypes.c_int32), ("views_total", ctypes.c_int32), ("max_views", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/boxfusion_b200.h

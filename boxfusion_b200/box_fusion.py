@@ -158,7 +158,7 @@ class BoxFusion(object):
         csr = ops.dev_tensor(np.concatenate([offsets, index]), torch.int32, dev)
         out, upd, its, _, status = ops.refine(
             self._pst_on(dev), boxes.tensor, boxes.R, per_frame_box.scores, per_frame_box.projected_boxes,
-            per_frame_box.cam_pose, csr[: len(todo) + 1], csr[len(todo) + 1:], self._rcfg(beta=beta))
+            per_frame_box.cam_pose, csr[: len(todo) + 1], csr[len(todo) + 1:], self._rcfg(beta=beta), max_views=max(lens))
         B = len(todo)
         flat = ops.to_host(torch.cat([out.reshape(-1), upd.to(torch.float32), its.to(torch.float32),
                                       status.to(torch.float32)]))                        # the call's single D2H

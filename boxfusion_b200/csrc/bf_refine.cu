@@ -19,36 +19,77 @@ namespace cg = cooperative_groups;
 
 struct P2 { float x, y; };
 
-#define BF_CAND_MAX 48          // reference buffer: 36 (box_fusion.py:378); overflow is reported, not UB
+#define BF_CAND_MAX 24          // reference buffer: 36 (box_fusion.py:378), observed maximum 14; overflow is reported, not UB
 #define BF_REFINE_THREADS 256
 
 __device__ __forceinline__ float bf_cross(const P2 o, const P2 a, const P2 b) {          // :74-76
     return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
 }
 
-// :95-145  sort by (x,y), monotone chain popping on cross <= 0, output lower[:-1] + upper[:-1]
-template <int NMAX>
-__device__ __forceinline__ int bf_hull2d(P2* __restrict__ p, int n, P2* __restrict__ out) {
+__device__ __forceinline__ bool bf_after(const P2 a, const P2 b) {                        // sort key of :105-106
+    return a.x > b.x || (a.x == b.x && a.y > b.y);
+}
+
+// Monotone chain over points already sorted by (x,y) (:114-141).  The stack lives in `out`; its top two
+// entries are mirrored in registers so that only a pop touches memory on the critical path.
+// GET(i) yields the i-th sorted point.  Output: lower[:-1] + upper[:-1], exactly the reference's order.
+#define BF_CHAIN(GET, n, out, total, UNROLL)                                                            \
+    {                                                                                             \
+        int nl_ = 0;                                                                              \
+        P2 a_ = {0.f, 0.f}, b_ = {0.f, 0.f};                                                      \
+        _Pragma(UNROLL)                                                                           \
+        for (int i_ = 0; i_ < (n); ++i_) {                                                        \
+            const P2 q_ = GET(i_);                                                                \
+            while (nl_ >= 2 && bf_cross(b_, a_, q_) <= 0) { --nl_; a_ = b_; if (nl_ >= 2) b_ = (out)[nl_ - 2]; } \
+            (out)[nl_] = q_; b_ = a_; a_ = q_; ++nl_;                                             \
+        }                                                                                         \
+        --nl_;                                                                                    \
+        P2* up_ = (out) + nl_;                                                                    \
+        int nu_ = 0;                                                                              \
+        _Pragma(UNROLL)                                                                           \
+        for (int i_ = (n) - 1; i_ >= 0; --i_) {                                                   \
+            const P2 q_ = GET(i_);                                                                \
+            while (nu_ >= 2 && bf_cross(b_, a_, q_) <= 0) { --nu_; a_ = b_; if (nu_ >= 2) b_ = up_[nu_ - 2]; } \
+            up_[nu_] = q_; b_ = a_; a_ = q_; ++nu_;                                               \
+        }                                                                                         \
+        --nu_;                                                                                    \
+        (total) = nl_ + nu_;                                                                      \
+    }
+
+// Hull of exactly 8 points held in registers: 19-comparator sorting network (same order as the
+// reference's exchange sort: equal keys are identical points), then the chain.  out needs 16 slots (the
+// upper chain grows transiently above the kept part of the lower chain).
+__device__ __forceinline__ int bf_hull8(P2 (&p)[8], P2* __restrict__ out) {
+#define BF_CE(i, j) { const bool sw_ = bf_after(p[i], p[j]); const P2 lo_ = sw_ ? p[j] : p[i]; const P2 hi_ = sw_ ? p[i] : p[j]; p[i] = lo_; p[j] = hi_; }
+    BF_CE(0, 1) BF_CE(2, 3) BF_CE(4, 5) BF_CE(6, 7)
+    BF_CE(0, 2) BF_CE(1, 3) BF_CE(4, 6) BF_CE(5, 7)
+    BF_CE(1, 2) BF_CE(5, 6) BF_CE(0, 4) BF_CE(3, 7)
+    BF_CE(1, 5) BF_CE(2, 6)
+    BF_CE(1, 4) BF_CE(3, 6)
+    BF_CE(2, 4) BF_CE(3, 5)
+    BF_CE(3, 4)
+#undef BF_CE
+    int total;
+#define BF_GET8(i) p[i]
+    BF_CHAIN(BF_GET8, 8, out, total, "unroll")
+#undef BF_GET8
+    return total;
+}
+
+// Hull of n points in memory (intersection candidates): insertion sort + chain (:95-145).  out needs 2n slots.
+__device__ __forceinline__ int bf_hull_n(P2* __restrict__ p, int n, P2* __restrict__ out) {
     if (n == 0) return 0;
     for (int i = 1; i < n; ++i) {
         const P2 k = p[i];
         int j = i - 1;
-        while (j >= 0 && (p[j].x > k.x || (p[j].x == k.x && p[j].y > k.y))) { p[j + 1] = p[j]; --j; }
+        while (j >= 0 && bf_after(p[j], k)) { p[j + 1] = p[j]; --j; }
         p[j + 1] = k;
     }
-    P2 up[NMAX];
-    int nl = 0, nu = 0;
-    for (int i = 0; i < n; ++i) {                       // lower chain is built directly in `out`
-        while (nl >= 2 && bf_cross(out[nl - 2], out[nl - 1], p[i]) <= 0) --nl;
-        out[nl++] = p[i];
-    }
-    for (int i = n - 1; i >= 0; --i) {
-        while (nu >= 2 && bf_cross(up[nu - 2], up[nu - 1], p[i]) <= 0) --nu;
-        up[nu++] = p[i];
-    }
-    --nl; --nu;
-    for (int i = 0; i < nu; ++i) out[nl + i] = up[i];
-    return nl + nu;
+    int total;
+#define BF_GETN(i) p[i]
+    BF_CHAIN(BF_GETN, n, out, total, "unroll 1")
+#undef BF_GETN
+    return total;
 }
 
 __device__ __forceinline__ float bf_shoelace(const P2* __restrict__ q, int n) {          // :148-156
@@ -60,68 +101,155 @@ __device__ __forceinline__ float bf_shoelace(const P2* __restrict__ q, int n) { 
     return fabsf(a) * 0.5f;                              // fabs(area)/2.0 is exact either way
 }
 
-__device__ __forceinline__ bool bf_seg_intersect(const P2 a1, const P2 a2, const P2 b1, const P2 b2, P2* out) {  // :159-177
+// line_intersection (:159-177).  Same doubles, same quotients; the divisions are skipped only where the
+// accept/reject decision cannot depend on their rounding:
+//   n < -1e-7*|den| or n > 1.0000001*|den|  -> the rounded quotient is outside [-1e-8, 1.00000001]
+//   0 <= n <= |den|                          -> the rounded quotient is inside [0, 1]
+// (numerator and denominator are negated together when den < 0: IEEE division is sign-symmetric).
+__device__ __forceinline__ bool bf_seg_intersect(const P2 a1, const P2 a2, const P2 b1, const P2 b2, P2* out) {
     const double dx1 = a2.x - a1.x, dy1 = a2.y - a1.y;
     const double dx2 = b2.x - b1.x, dy2 = b2.y - b1.y;
     const double den = dx1 * dy2 - dy1 * dx2;
-    if (fabs(den) < 1e-8) return false;
+    const double d = fabs(den);
+    if (d < 1e-8) return false;
     const double e1 = a1.y - b1.y, e2 = b1.x - a1.x;     // float differences widened to double
-    const double t = (dx2 * e1 + dy2 * e2) / den;
-    const double s = (dx1 * e1 + dy1 * e2) / den;
-    if (t >= -1e-8 && t <= 1.00000001 && s >= -1e-8 && s <= 1.00000001) {
-        out->x = (float)(a1.x + t * dx1);
-        out->y = (float)(a1.y + t * dy1);
-        return true;
+    double nt = dx2 * e1 + dy2 * e2;
+    double ns = dx1 * e1 + dy1 * e2;
+    if (den < 0) { nt = -nt; ns = -ns; }
+    const double lo = -1e-7 * d, hi = 1.0000001 * d;
+    if (nt < lo || nt > hi || ns < lo || ns > hi) return false;
+    const double t = nt / d;
+    if (!(nt >= 0 && nt <= d) && !(t >= -1e-8 && t <= 1.00000001)) return false;
+    if (!(ns >= 0 && ns <= d)) {
+        const double s_ = ns / d;
+        if (!(s_ >= -1e-8 && s_ <= 1.00000001)) return false;
     }
-    return false;
+    out->x = (float)(a1.x + t * dx1);
+    out->y = (float)(a1.y + t * dy1);
+    return true;
 }
 
-__device__ __forceinline__ bool bf_inside_poly(const P2 p, const P2* __restrict__ q, int n) {   // :180-199
-    bool in = false;
-    for (int i = 0; i < n; ++i) {
-        const P2 p1 = q[i], p2 = q[(i + 1 == n) ? 0 : i + 1];
-        if ((p1.y > p.y) != (p2.y > p.y)) {
-            const float xi = ((p.y - p1.y) * (p2.x - p1.x) / (p2.y - p1.y)) + p1.x;
-            if (p.x < xi) in = !in;
+// One edge of the even-odd ray cast (:186-196).  x_inters lies within a few ulps of [min(p1.x,p2.x),
+// max(p1.x,p2.x)], so half a pixel of margin decides most edges without the division.
+__device__ __forceinline__ bool bf_ray_edge(const P2 p, const P2 p1, const P2 p2) {
+    if ((p1.y > p.y) == (p2.y > p.y)) return false;
+    if (p.x < fminf(p1.x, p2.x) - 0.5f) return true;
+    if (p.x > fmaxf(p1.x, p2.x) + 0.5f) return false;
+    const float xi = ((p.y - p1.y) * (p2.x - p1.x) / (p2.y - p1.y)) + p1.x;
+    return p.x < xi;
+}
+
+struct bf_view {            // per-view constants staged in shared memory
+    float4 ebb[8];          // bounding box of every edge of the observation hull (xmin, ymin, xmax, ymax)
+    float pose[12];         // rows 0..2 of the camera->world 4x4
+    P2 hull[8];
+    float bb[4];            // bounding box of the observation hull (xmin, ymin, xmax, ymax)
+    int nt;
+    float area_t;
+};
+
+// fill the derived fields of a view once its hull is known
+__device__ __forceinline__ void bf_view_finish(bf_view& vw, const P2* ht) {
+    for (int k = 0; k < 8; ++k) vw.hull[k] = ht[k < vw.nt ? k : 0];
+    vw.area_t = bf_shoelace(ht, vw.nt);
+    float x0 = 1e30f, y0 = 1e30f, x1 = -1e30f, y1 = -1e30f;
+    for (int k = 0; k < vw.nt; ++k) { x0 = fminf(x0, ht[k].x); x1 = fmaxf(x1, ht[k].x); y0 = fminf(y0, ht[k].y); y1 = fmaxf(y1, ht[k].y); }
+    vw.bb[0] = x0; vw.bb[1] = y0; vw.bb[2] = x1; vw.bb[3] = y1;
+    for (int k = 0; k < 8; ++k) {
+        const P2 b1 = vw.hull[k < vw.nt ? k : 0], b2 = vw.hull[(k + 1 < vw.nt) ? k + 1 : 0];
+        vw.ebb[k] = make_float4(fminf(b1.x, b2.x), fminf(b1.y, b2.y), fmaxf(b1.x, b2.x), fmaxf(b1.y, b2.y));
+    }
+}
+
+// IoU of the particle's projected hull (registers, n0 vertices) against the view's observation hull (:380-398).
+// Exact pruning (the decisions below cannot differ from the reference's arithmetic):
+//   * a vertex outside the other polygon's bounding box (0.01 px of slack in x, where the crossing abscissa is a
+//     rounded quantity) is outside the polygon for the even-odd ray cast: no edge straddles its y, or every crossing
+//     lies on one side of it and a closed polygon is crossed an even number of times;
+//   * two edges whose bounding boxes are more than 0.01 px apart cannot intersect: the float64 quotients t, s are
+//     accurate to ~1e-15 (all products of float differences are exact in double), and the accepted parameter range
+//     [-1e-8, 1.00000001] extends an edge by less than 1e-4 px.
+__device__ __forceinline__ float bf_hull_iou(const P2 (&h0)[8], const P2* __restrict__ hl, int n0, const bf_view& vw,
+                                             int* overflow) {
+    const P2* __restrict__ ht = vw.hull;
+    const int nt = vw.nt;
+    P2 cand[BF_CAND_MAX], hi[2 * BF_CAND_MAX];
+    int nc = 0;
+    // bounding box of h0 (hull vertices beyond n0 are ignored)
+    float x0 = h0[0].x, x1 = h0[0].x, y0 = h0[0].y, y1 = h0[0].y;
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+        if (i < n0) { x0 = fminf(x0, h0[i].x); x1 = fmaxf(x1, h0[i].x); y0 = fminf(y0, h0[i].y); y1 = fmaxf(y1, h0[i].y); }
+    // vertices of h0 inside ht (:210-214)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < n0) {
+            const P2 q = h0[i];
+            if (q.x >= vw.bb[0] - 0.01f && q.x <= vw.bb[2] + 0.01f && q.y >= vw.bb[1] && q.y <= vw.bb[3]) {
+                bool in = false;
+                for (int j = 0; j < nt; ++j) in ^= bf_ray_edge(q, ht[j], ht[(j + 1 == nt) ? 0 : j + 1]);
+                if (in) { cand[nc] = q; ++nc; }
+            }
         }
     }
-    return in;
-}
-
-// IoU of the particle's projected hull h0 against the view's observation hull ht (:380-398).
-__device__ __forceinline__ float bf_hull_iou(const P2* __restrict__ h0, int n0, const P2* __restrict__ ht, int nt,
-                                             float area_t, int* overflow) {
-    P2 cand[BF_CAND_MAX], hi[BF_CAND_MAX];
-    int nc = 0;
-    for (int i = 0; i < n0; ++i) if (bf_inside_poly(h0[i], ht, nt)) { if (nc < BF_CAND_MAX) cand[nc] = h0[i]; ++nc; }
-    for (int i = 0; i < nt; ++i) if (bf_inside_poly(ht[i], h0, n0)) { if (nc < BF_CAND_MAX) cand[nc] = ht[i]; ++nc; }
-    for (int i = 0; i < n0; ++i) {
-        const P2 a1 = h0[i], a2 = h0[(i + 1 == n0) ? 0 : i + 1];
-        for (int j = 0; j < nt; ++j) {
-            P2 x;
-            if (bf_seg_intersect(a1, a2, ht[j], ht[(j + 1 == nt) ? 0 : j + 1], &x)) { if (nc < BF_CAND_MAX) cand[nc] = x; ++nc; }
+    // vertices of ht inside h0 (:215-219)
+    for (int i = 0; i < nt; ++i) {
+        const P2 q = ht[i];
+        if (q.x >= x0 - 0.01f && q.x <= x1 + 0.01f && q.y >= y0 && q.y <= y1) {
+            bool in = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < n0) in ^= bf_ray_edge(q, h0[j], (j + 1 < n0) ? h0[(j + 1) & 7] : h0[0]);
+            if (in) { cand[nc] = q; ++nc; }
+        }
+    }
+    // edge x edge intersections (:222-236), two phases so that a warp does not execute the float64 test for every
+    // (i, j) any lane needs: (1) branch-free bounding-box filter -> per-thread bit mask of surviving pairs, bit 8*i+j;
+    // (2) loop over the survivors in the reference's (i, j) order.
+    const float m = 0.01f;
+    unsigned long long pairs = 0ull;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const P2 a1 = h0[i], a2 = (i + 1 < n0) ? h0[(i + 1) & 7] : h0[0];
+        const float ax0 = fminf(a1.x, a2.x) - m, ax1 = fmaxf(a1.x, a2.x) + m, ay0 = fminf(a1.y, a2.y) - m, ay1 = fmaxf(a1.y, a2.y) + m;
+        unsigned row = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 eb = vw.ebb[j];                         // edge j of ht: (xmin, ymin, xmax, ymax)
+            const bool hit = !(ax0 > eb.z || ax1 < eb.x || ay0 > eb.w || ay1 < eb.y) && (j < nt);
+            row |= hit ? (1u << j) : 0u;
+        }
+        if (i < n0) pairs |= (unsigned long long)row << (8 * i);
+    }
+    while (pairs) {
+        const int bit = __ffsll((long long)pairs) - 1;
+        pairs &= pairs - 1;
+        const int i = bit >> 3, j = bit & 7;
+        const P2 a1 = hl[i], a2 = hl[(i + 1 == n0) ? 0 : i + 1];   // same vertices as h0[], read with a dynamic index
+        P2 x;
+        if (bf_seg_intersect(a1, a2, ht[j], ht[(j + 1 == nt) ? 0 : j + 1], &x)) {
+            if (nc < BF_CAND_MAX) cand[nc] = x;
+            ++nc;
         }
     }
     if (nc > BF_CAND_MAX) { *overflow = 1; nc = BF_CAND_MAX; }
-    const int ni = bf_hull2d<BF_CAND_MAX>(cand, nc, hi);
-    const float ai = bf_shoelace(hi, ni), a0 = bf_shoelace(h0, n0);
-    const float uni = a0 + area_t - ai;
+    const int ni = bf_hull_n(cand, nc, hi);
+    const float ai = bf_shoelace(hi, ni);
+    float a0 = 0.0f;                                    // polygon_area(convex_0), vertices in registers
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < n0) { const P2 p1 = h0[i], p2 = (i + 1 < n0) ? h0[(i + 1) & 7] : h0[0]; a0 += p1.x * p2.y - p2.x * p1.y; }
+    a0 = fabsf(a0) * 0.5f;
+    const float uni = a0 + vw.area_t - ai;
     float iou = 0;
     if (uni > 0) iou = (float)((double)ai / ((double)uni + 0.00001));
     return iou;
 }
 
-struct bf_view {            // per-view constants staged in shared memory
-    float pose[12];         // rows 0..2 of the camera->world 4x4
-    P2 hull[8];
-    int nt;
-    float area_t;
-};
-
 // One (particle, view) term |1 - iou| from the particle's world corners (:345-400).
 __device__ __forceinline__ float bf_eval_view(const float (*c)[3], const bf_view& vw, float fx, float cx, float fy,
                                               float cy, float img_w, float img_h, int* overflow) {
-    P2 uv[8], h0[8];
+    P2 uv[8];
     const float* ps = vw.pose;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -134,8 +262,12 @@ __device__ __forceinline__ float bf_eval_view(const float (*c)[3], const bf_view
         uv[j].x = (px > img_w) ? img_w : (px < 0) ? 0 : px;
         uv[j].y = (py > img_h) ? img_h : (py < 0) ? 0 : py;
     }
-    const int n0 = bf_hull2d<8>(uv, 8, h0);
-    const float iou = bf_hull_iou(h0, n0, vw.hull, vw.nt, vw.area_t, overflow);
+    P2 hm[16];
+    const int n0 = bf_hull8(uv, hm);
+    P2 h0[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h0[k] = hm[k];            // hull vertices back into registers (static indices)
+    const float iou = bf_hull_iou(h0, hm, n0, vw, overflow);
     return fabsf(1 - iou);
 }
 
@@ -205,15 +337,14 @@ struct bf_refine_state {     // optimiser state of one box; the cluster leader's
 };
 
 // ---- shared-memory layout (identical in every CTA of a cluster so that DSMEM offsets match) ------------
-struct bf_refine_smem {
+struct __align__(16) bf_refine_smem {
     bf_refine_state S;
-    bf_view views[BF_MAX_VIEWS];
     int warp_cnt[32];
     float vbox[6 * BF_MAX_VIEWS];        // gathered view boxes (init_opt_params)
     float vscore[BF_MAX_VIEWS];
     float col[3 * BF_MAX_VIEWS];
     int overflow;
-    // followed by: float fit[P]; int sel[max_hits]; float contrib[pair_cap]
+    // followed by: bf_view views[max_views]; float fit[P]; int sel[max_hits]; float contrib[pair_cap]
 };
 
 extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
@@ -221,11 +352,10 @@ extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
 // One thread-block CLUSTER per map box.  Work items of an optimiser iteration are spread over all CTAs of
 // the cluster; every CTA writes its results straight into the leader's shared memory (DSMEM), the leader
 // reduces in the reference's order and publishes the new state, two cluster barriers per iteration.
-//   pair mode     (n_eval*V <= pair_cap): one work item = one (particle, view); contributions are stored
-//                 view-major and summed per particle in ascending view order by the leader
-//   particle mode (larger problems): one work item = one particle, views summed sequentially in registers
+// One work item = one (view, particle); contributions are stored view-major and summed per particle in ascending
+// view order by the leader (the reference's host order of the atomicAdd sum).
 __global__ void __launch_bounds__(BF_REFINE_THREADS, 2)
-bf_refine_kernel(const bf_refine_params prm, int pair_cap) {
+bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float* __restrict__ gcontrib) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks();
     const unsigned crank = cluster.block_rank();
@@ -237,12 +367,12 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap) {
     const bf_refine_cfg& cfg = prm.cfg;
     bf_refine_smem* sm = (bf_refine_smem*)bf_refine_smem_raw;
     bf_refine_state* S = &sm->S;
-    bf_view* views = sm->views;
-    float* fit = (float*)(sm + 1);
+    bf_view* views = (bf_view*)(sm + 1);
+    float* fit = (float*)(views + max_views);
     int* sel = (int*)(fit + prm.P);
     float* contrib = (float*)(sel + cfg.max_hits);
     if (tid == 0) sm->overflow = 0;
-    if (V < 1 || V > BF_MAX_VIEWS) {                     // flagged in status by bf_check_views_kernel2 (cluster-uniform)
+    if (V < 1 || V > max_views) {                        // flagged in status by bf_check_views_kernel2 (cluster-uniform)
         if (tid == 0 && crank == 0) { prm.out_updated[b] = 0; prm.out_iters[b] = 0; }
         return;
     }
@@ -260,10 +390,9 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap) {
         P2 t[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { t[k].x = prm.per_uv[16 * (size_t)m + 2 * k]; t[k].y = prm.per_uv[16 * (size_t)m + 2 * k + 1]; }
-        P2 ht[8];
-        vw.nt = bf_hull2d<8>(t, 8, ht);
-        for (int k = 0; k < 8; ++k) vw.hull[k] = ht[k < vw.nt ? k : 0];
-        vw.area_t = bf_shoelace(ht, vw.nt);
+        P2 ht[16];
+        vw.nt = bf_hull8(t, ht);
+        bf_view_finish(vw, ht);
 #pragma unroll
         for (int k = 0; k < 6; ++k) sm->vbox[6 * v + k] = prm.per_xyzlhw[6 * (size_t)m + k];
         sm->vscore[v] = prm.per_scores[m];
@@ -299,49 +428,35 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap) {
     __syncthreads();
 
     const int n_eval = min(32 * (cfg.pst_size / 32), prm.P);
-    const bool pair_mode = (long long)n_eval * V <= (long long)pair_cap;
+    // contributions |1-iou| of every (view, particle), view-major.  Small problems keep them in the leader's shared
+    // memory (written through DSMEM); large ones (C4: 4096 x 32) use an L2-resident global scratch slab of this box.
+    const bool in_smem = (long long)n_eval * V <= (long long)pair_cap;
+    float* wcontrib = in_smem ? l_contrib : gcontrib + (size_t)v0 * n_eval;        // where this CTA writes
+    const float* rcontrib = in_smem ? contrib : gcontrib + (size_t)v0 * n_eval;    // where the leader reads
     const float beta = (float)cfg.beta, omb = (float)(1.0 - cfg.beta);
     int overflow = 0;
     int it = 0;
     cluster.sync();                                      // every CTA's shared memory is initialised
     for (int n = 0; n < cfg.iters; ++n) {
-        // ---- evaluate_iou (:413-461) spread over the cluster ------------------------------------------------
-        if (pair_mode) {
-            const int items = n_eval * V;
-            for (int w = crank * T + tid; w < items; w += C * T) {
-                const int v = w / n_eval, p = w - v * n_eval;          // view-major: a warp works on one view
-                float pst6[6];
+        // ---- evaluate_iou (:413-461): one work item = one (view, particle), spread over the whole cluster ----
+        const int items = n_eval * V;
+        for (int w = crank * T + tid; w < items; w += C * T) {
+            const int v = w / n_eval, p = w - v * n_eval;              // view-major: a warp works on one view
+            float pst6[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
-                float c[8][3];
-                bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
-                l_contrib[w] = bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
-            }
-        } else {
-            for (int p = crank * T + tid; p < n_eval; p += C * T) {
-                float pst6[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
-                float c[8][3];
-                bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
-                float value = 0.0f, count = 0.0f;
-                for (int v = 0; v < V; ++v) {           // ascending views: the host order of the atomicAdd sum (:400)
-                    value += bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
-                    count += 1;
-                }
-                l_fit[p] = value / (count + 1e-6f);     // :454
-            }
+            for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
+            float c[8][3];
+            bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
+            wcontrib[w] = bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
         }
         ++it;
         cluster.sync();
         if (crank == 0) {
             // ---- fitness per particle, views summed in ascending order (:400-401, :454) ---------------------
-            if (pair_mode) {
-                for (int p = tid; p < n_eval; p += T) {
-                    float value = 0.0f, count = 0.0f;
-                    for (int v = 0; v < V; ++v) { value += contrib[v * n_eval + p]; count += 1; }
-                    fit[p] = value / (count + 1e-6f);
-                }
+            for (int p = tid; p < n_eval; p += T) {
+                float value = 0.0f, count = 0.0f;
+                for (int v = 0; v < V; ++v) { value += rcontrib[v * n_eval + p]; count += 1; }
+                fit[p] = value / (count + 1e-6f);
             }
             for (int p = n_eval + tid; p < prm.P; p += T) fit[p] = 0.0f / (0.0f + 1e-6f);   // never launched
             __syncthreads();
@@ -435,19 +550,20 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap) {
     }
 }
 
-#define BF_PAIR_CAP 16384      // (particle, view) contributions the leader can hold: 64 KB
+#define BF_PAIR_CAP 8192       // (view, particle) contributions the leader holds in shared memory: 32 KB
 
-static size_t bf_refine_smem_bytes(int P, int max_hits, int pair_cap) {
-    return sizeof(bf_refine_smem) + sizeof(float) * (size_t)P + sizeof(int) * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + 16;
+static size_t bf_refine_smem_bytes(int P, int max_hits, int pair_cap, int max_views) {
+    return sizeof(bf_refine_smem) + sizeof(bf_view) * (size_t)max_views + sizeof(float) * (size_t)P +
+           sizeof(int) * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + 16;
 }
 
 __global__ void bf_check_views_kernel(const int32_t* __restrict__ off, int B, int32_t* __restrict__ status) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) status[0] = 0;
 }
-__global__ void bf_check_views_kernel2(const int32_t* __restrict__ off, int B, int32_t* __restrict__ status) {
+__global__ void bf_check_views_kernel2(const int32_t* __restrict__ off, int B, int max_views, int32_t* __restrict__ status) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) { const int V = off[b + 1] - off[b]; if (V < 1 || V > BF_MAX_VIEWS) atomicExch(status, BF_ERR_CAPACITY); }
+    if (b < B) { const int V = off[b + 1] - off[b]; if (V < 1 || V > max_views) atomicExch(status, BF_ERR_CAPACITY); }
 }
 
 extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per_xyzlhw, const float* per_R,
@@ -464,20 +580,32 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
         !out_xyzlhw || !out_updated || !out_iters)
         return bf_fail(h, BF_ERR_INVALID_ARG, "bf_refine", "null pointer");
     if (cfg->max_hits < 1 || cfg->max_hits > 4096 || cfg->iters < 1) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_refine", "bad cfg");
-    bf_check_views_kernel2<<<bf_blocks(B, 128), 128, 0, st>>>(view_offsets, B, status);
+    const int max_views = (cfg->max_views > 0 && cfg->max_views <= BF_MAX_VIEWS) ? cfg->max_views : BF_MAX_VIEWS;
+    bf_check_views_kernel2<<<bf_blocks(B, 128), 128, 0, st>>>(view_offsets, B, max_views, status);
     bf_refine_params prm;
     prm.pst = pst; prm.P = P; prm.per_xyzlhw = per_xyzlhw; prm.per_R = per_R; prm.per_scores = per_scores;
     prm.per_uv = per_uv; prm.per_poses = per_poses; prm.view_offsets = view_offsets; prm.view_index = view_index;
     prm.B = B; prm.cfg = *cfg; prm.out_xyzlhw = out_xyzlhw; prm.out_updated = out_updated; prm.out_iters = out_iters;
     prm.trace = trace; prm.status = status;
-    const int pair_cap = BF_PAIR_CAP;
-    const size_t smem = bf_refine_smem_bytes(P, cfg->max_hits, pair_cap);
+    // shared memory is sized per launch (what is not shared memory is L1 for the per-thread polygon buffers):
+    // contributions live in the leader's shared memory only when every box of the call fits BF_PAIR_CAP
+    const int n_eval0 = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
+    const int pair_cap = ((long long)n_eval0 * max_views <= BF_PAIR_CAP) ? n_eval0 * max_views : 0;
+    const size_t smem = bf_refine_smem_bytes(P, cfg->max_hits, pair_cap, max_views);
+    // global contribution scratch: sum(V) * n_eval floats (only touched by boxes that do not fit shared memory)
+    void* gscratch = nullptr;
+    {
+        const long long n_eval_h = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
+        const long long views_total = cfg->views_total > 0 ? (long long)cfg->views_total : (long long)B * BF_MAX_VIEWS;
+        int rc = bf_scratch(h, BF_SCRATCH_REFINE, sizeof(float) * (size_t)(views_total * n_eval_h), &gscratch);
+        if (rc) return rc;
+    }
     BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     // cluster size: enough CTAs that a box's work items are ~2 per thread, as long as the whole launch still
     // fits the machine about twice over (2 CTAs of 256 threads per SM)
     const int n_eval = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
-    const long long hint_items = (long long)n_eval * (cfg->views_hint > 0 ? cfg->views_hint : 8);
+    const long long hint_items = (long long)n_eval * (cfg->views_total > 0 ? (cfg->views_total + B - 1) / B : 8);
     int C = 1;
     while (C < 16 && (long long)C * BF_REFINE_THREADS * 2 < hint_items) C *= 2;
     while (C > 1 && (long long)B * C > 4LL * h->sm_count) C /= 2;
@@ -491,7 +619,7 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
         int nclusters = 0;
         cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, bf_refine_kernel, &lc);
         if ((e != cudaSuccess || nclusters < 1) && C > 1) { cudaGetLastError(); continue; }
-        e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap);
+        e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap, max_views, (float*)gscratch);
         if (e != cudaSuccess) {
             if (C > 1) { cudaGetLastError(); continue; }
             return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
@@ -513,11 +641,11 @@ bf_evaluate_kernel(const float* __restrict__ pst, int P, const float* __restrict
     for (int v = tid; v < V; v += blockDim.x) {
         bf_view& vw = views[v];
         for (int k = 0; k < 12; ++k) vw.pose[k] = poses[16 * v + k];
-        P2 t[8], ht[8];
+        P2 t[8], ht[16];
+#pragma unroll
         for (int k = 0; k < 8; ++k) { t[k].x = uv[16 * v + 2 * k]; t[k].y = uv[16 * v + 2 * k + 1]; }
-        vw.nt = bf_hull2d<8>(t, 8, ht);
-        for (int k = 0; k < 8; ++k) vw.hull[k] = ht[k < vw.nt ? k : 0];
-        vw.area_t = bf_shoelace(ht, vw.nt);
+        vw.nt = bf_hull8(t, ht);
+        bf_view_finish(vw, ht);
     }
     if (tid == 0) {
         for (int k = 0; k < 6; ++k) { S.box6[k] = box6[k]; S.search[k] = search6[k]; }

@@ -201,11 +201,11 @@ def make_refine_cfg(cfg: dict, K16, img_h: float, img_w: float, beta: float = 0.
                      float(ro["center_init_size"]), float(ro["shape_init_size"]),
                      float(ro["center_scaling_coefficient"]), float(ro["shape_scaling_coefficient"]),
                      float(beta), float(img_h), float(img_w),
-                     float(K16[0]), float(K16[2]), float(K16[5]), float(K16[6]), int(max_hits), int(bool(early_stop)), 0)
+                     float(K16[0]), float(K16[2]), float(K16[5]), float(K16[6]), int(max_hits), int(bool(early_stop)), 0, 0)
 
 
 def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, view_index, rcfg: RefineCfg,
-           want_trace: bool = False):
+           want_trace: bool = False, max_views: int = 0):
     """BoxFusion.boxfusion optimiser for B boxes in one launch (box_fusion.py:651-721).
     Returns (out_xyzlhw[B,6] f32, updated[B] i32, iters[B] i32, trace|None, status[1] i32), all on the device."""
     dev = _pick_device(per_xyzlhw, pst)
@@ -218,8 +218,8 @@ def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, 
     off = dev_tensor(view_offsets, torch.int32, dev).reshape(-1)
     idx = dev_tensor(view_index, torch.int32, dev).reshape(-1)
     B = off.shape[0] - 1
-    if B > 0 and rcfg.views_hint == 0:
-        rcfg.views_hint = max(1, int(round(idx.shape[0] / B)))
+    rcfg.views_total = int(idx.shape[0])
+    rcfg.max_views = int(max_views)
     out = torch.empty((B, 6), dtype=torch.float32, device=dev)
     upd = torch.empty(B, dtype=torch.int32, device=dev)
     its = torch.empty(B, dtype=torch.int32, device=dev)

@@ -123,7 +123,8 @@ typedef struct {
     float fx, cx, fy, cy;     /* K[0],K[2],K[5],K[6] of the flattened 4x4 (box_fusion.py:356-357) */
     int32_t max_hits;         /* 200                                                     */
     int32_t early_stop;       /* 1: stop after 3 consecutive failures (reference); 0: run all iters */
-    int32_t views_hint;       /* typical views per box of this call (0 = unknown): sizes the thread-block cluster */
+    int32_t views_total;      /* entries of view_index (= view_offsets[B]); 0 = unknown (scratch is sized for BF_MAX_VIEWS per box) */
+    int32_t max_views;        /* largest number of views of any box in this call; 0 = unknown (BF_MAX_VIEWS) */
 } bf_refine_cfg;
 
 int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_refine_cfg_layout_matches_header():
-    assert ctypes_sizeof() == 72
+    assert ctypes_sizeof() == 72          # 17 x 4-byte fields + one double, padded to 8
 
 
 def ctypes_sizeof():
