@@ -41,8 +41,8 @@ GOLDEN_PST = os.path.join(ROOT, "tests", "golden", "pst_1024_0.npy")
 FRAMES_PER_SEQUENCE = 300
 N_OBJECTS, MAX_DET = 200, 50
 # algorithmic FP32 work of one (particle, view) evaluation of compute_iou_value, counted on the straight-line
-# path of bf_eval_view for two hexagonal hulls with 6 intersection candidates (DESIGN.md section "Kernels")
-FLOP_PER_EVAL = 1900.0
+# path of bf_eval_view for two hexagonal hulls with 6-8 intersection candidates (table in DESIGN.md section 4, K3)
+FLOP_PER_EVAL = 1600.0
 # bytes one evaluation must touch: nothing in HBM (PST row and view constants are on chip); 4 B of fitness per particle
 BYTES_PER_EVAL = 0.5
 
@@ -193,14 +193,9 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         t_res, t_e2e = float(tt[0]), float(tt[1])
         # the only exchange of the job: gather every rank's final map (rows of 15 floats), SURVEY section 8(e)
-        m = torch.cat([sess.all_pred_box.pred_boxes_3d.tensor, sess.all_pred_box.pred_boxes_3d.R.reshape(-1, 9)], 1)
-        n_rows = torch.tensor([m.shape[0]], device=dev)
-        sizes = [torch.zeros_like(n_rows) for _ in range(world)]
-        torch.distributed.all_gather(sizes, n_rows)
-        pad = torch.zeros((int(max(s.item() for s in sizes)), 15), device=dev)
-        pad[: m.shape[0]] = m
-        maps = [torch.zeros_like(pad) for _ in range(world)]
-        torch.distributed.all_gather(maps, pad)
+        from boxfusion_b200.sharding import gather_maps, map_rows
+        maps = gather_maps(map_rows(sess.all_pred_box))
+        assert len(maps) == world
     if rank != 0:
         return None
     total_frames = K * world

@@ -14,6 +14,7 @@ prints and re-indexes them.  The decisions that fill them are taken on the GPU:
 from __future__ import annotations
 
 import copy
+import itertools
 from typing import Dict, List
 
 import numpy as np
@@ -29,6 +30,7 @@ class BoxManager:
         self.last_fusion_frame: List[List[int]] = []
         self.fusion_flag: List[int] = []
         self.already_fusion: List[List[int]] = []
+        self._fused_set, self._fused_n = set(), 0
         self.num_record: Dict[int, int] = {}
         self.cfg = cfg
         self.rotation_gap = self.cfg["association"]["rotation_gap"]
@@ -47,7 +49,12 @@ class BoxManager:
         self.already_fusion.append(copy.deepcopy(idx_list))
 
     def check_if_fusion(self, idx_list):
-        return idx_list in self.already_fusion
+        """`idx_list in self.already_fusion` (box_manager.py:34-38) through a set of tuples kept in step with the
+        public list (rebuilt if a caller edited `already_fusion` directly)."""
+        if self._fused_n != len(self.already_fusion):
+            self._fused_set = {tuple(int(x) for x in l) for l in self.already_fusion}
+            self._fused_n = len(self.already_fusion)
+        return tuple(int(x) for x in idx_list) in self._fused_set
 
     def update(self, keep_idx):
         self.fusion_list = [self.fusion_list[i] for i in keep_idx]
@@ -75,14 +82,16 @@ class BoxManager:
     def pack_lists(self, n: int):
         """fusion_list/fusion_flag of the first n boxes -> (list[n,CAP] i32, len[n] i32, flag[n] i32) numpy."""
         cap = ops.FUSION_CAP
+        lists = self.fusion_list[:n]
+        ln = np.fromiter(map(len, lists), dtype=np.int32, count=n)
+        if n and ln.max() > cap:
+            raise RuntimeError(f"a fusion list has {int(ln.max())} entries; device capacity is {cap}")
         fl = np.zeros((n, cap), dtype=np.int32)
-        ln = np.zeros(n, dtype=np.int32)
-        for i in range(n):
-            l = self.fusion_list[i]
-            if len(l) > cap:
-                raise RuntimeError(f"fusion list of box {i} has {len(l)} entries; device capacity is {cap}")
-            ln[i] = len(l)
-            fl[i, :len(l)] = l
+        total = int(ln.sum())
+        flat = np.fromiter(itertools.chain.from_iterable(lists), dtype=np.int64, count=total)
+        rows = np.repeat(np.arange(n), ln)
+        cols = np.arange(total) - np.repeat(np.cumsum(ln) - ln, ln)
+        fl[rows, cols] = flat
         flag = np.asarray(self.fusion_flag[:n], dtype=np.int32)
         return fl, ln, flag
 

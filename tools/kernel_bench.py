@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from boxfusion_b200 import ops                                                  # noqa: E402
 from boxfusion_b200.synthetic import make_cfg, make_pst, map_and_detections, refine_problem  # noqa: E402
 
-FLOP_PER_EVAL = 1900.0
+FLOP_PER_EVAL = 1600.0
 
 
 def timeit(fn, reps=5, warm=3):
