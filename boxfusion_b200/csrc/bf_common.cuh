@@ -28,7 +28,9 @@ struct bf_handle {
     char err[512];
     void* buf[BF_SCRATCH_SLOTS];
     size_t cap[BF_SCRATCH_SLOTS];
-    int last_refine_cluster;    // cluster size the last bf_refine launch used (diagnostic)
+    int last_refine_cluster;    // cluster size * 1000 + block size of the last bf_refine launch (diagnostic)
+    int refine_occ[20];         // cached cudaOccupancyMaxActiveClusters answers per (cluster size, block size)
+    long long refine_occ_smem[20];   // dynamic shared memory (+1) the cached answer was computed for
 };
 
 static inline int bf_fail(bf_handle* h, int code, const char* what, const char* detail) {

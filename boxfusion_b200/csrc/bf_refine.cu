@@ -20,7 +20,7 @@ namespace cg = cooperative_groups;
 struct P2 { float x, y; };
 
 #define BF_CAND_MAX 24          // reference buffer: 36 (box_fusion.py:378), observed maximum 14; overflow is reported, not UB
-#define BF_REFINE_THREADS 256
+#define BF_REFINE_THREADS 512    // upper bound of the block size; the launch picks 128..512 per call
 
 __device__ __forceinline__ float bf_cross(const P2 o, const P2 a, const P2 b) {          // :74-76
     return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
@@ -354,7 +354,7 @@ extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
 // reduces in the reference's order and publishes the new state, two cluster barriers per iteration.
 // One work item = one (view, particle); contributions are stored view-major and summed per particle in ascending
 // view order by the leader (the reference's host order of the atomicAdd sum).
-__global__ void __launch_bounds__(BF_REFINE_THREADS, 2)
+__global__ void __launch_bounds__(BF_REFINE_THREADS, 1)
 bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float* __restrict__ gcontrib) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks();
@@ -591,7 +591,8 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
     // contributions live in the leader's shared memory only when every box of the call fits BF_PAIR_CAP
     const int n_eval0 = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
     const int pair_cap = ((long long)n_eval0 * max_views <= BF_PAIR_CAP) ? n_eval0 * max_views : 0;
-    const size_t smem = bf_refine_smem_bytes(P, cfg->max_hits, pair_cap, max_views);
+    // rounded up to 8 KB so that the cached occupancy answers below are reused across keyframes
+    const size_t smem = (bf_refine_smem_bytes(P, cfg->max_hits, pair_cap, max_views) + 8191) / 8192 * 8192;
     // global contribution scratch: sum(V) * n_eval floats (only touched by boxes that do not fit shared memory)
     void* gscratch = nullptr;
     {
@@ -602,30 +603,57 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
     }
     BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    // cluster size: enough CTAs that a box's work items are ~2 per thread, as long as the whole launch still
-    // fits the machine about twice over (2 CTAs of 256 threads per SM)
-    const int n_eval = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
-    const long long hint_items = (long long)n_eval * (cfg->views_total > 0 ? (cfg->views_total + B - 1) / B : 8);
-    int C = 1;
-    while (C < 16 && (long long)C * BF_REFINE_THREADS * 2 < hint_items) C *= 2;
-    while (C > 1 && (long long)B * C > 4LL * h->sm_count) C /= 2;
-    for (;; C /= 2) {
+    // Launch shape.  A box's optimiser iteration has items = n_eval * V independent evaluations followed by a short
+    // leader phase, so its latency is passes = ceil(items / (C*T)) evaluations; B boxes need waves = ceil(B / clusters
+    // that fit the machine).  Pick the (cluster size C, block size T) that minimises waves * passes, preferring fewer
+    // threads on ties.  Occupancy answers are cached in the handle.
+    const int n_eval = n_eval0;
+    const long long items = (long long)n_eval * (cfg->views_total > 0 ? (cfg->views_total + B - 1) / B : max_views);
+    static const int Cs[5] = {16, 8, 4, 2, 1};
+    static const int Ts[4] = {512, 384, 256, 128};
+    int bestC = 1, bestT = 256;
+    double best_cost = 1e300;
+    // throughput regime (the call alone fills the machine): 256-thread CTAs, two per SM so that one box's leader phase
+    // and cluster barriers overlap another box's evaluations; cluster just large enough for ~2 items per thread
+    const bool saturated = (double)B * (double)items >= (double)h->sm_count * 512.0;
+    if (saturated) {
+        bestT = 256;
+        while (bestC < 16 && (long long)bestC * bestT * 2 < items) bestC *= 2;
+        while (bestC > 1 && (long long)B * bestC > 4LL * h->sm_count) bestC /= 2;
+        best_cost = 0.0;
+    }
+    for (int ci = 0; ci < 5 && !saturated; ++ci)
+        for (int ti = 0; ti < 4; ++ti) {
+            const int C = Cs[ci], T = Ts[ti];
+            int active = 0;
+            const int slot = ci * 4 + ti;
+            if (h->refine_occ_smem[slot] == (long long)smem + 1) active = h->refine_occ[slot];
+            else {
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3((unsigned)(C * 64)); lc.blockDim = dim3(T); lc.dynamicSmemBytes = smem; lc.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                if (cudaOccupancyMaxActiveClusters(&active, bf_refine_kernel, &lc) != cudaSuccess) { cudaGetLastError(); active = 0; }
+                h->refine_occ[slot] = active; h->refine_occ_smem[slot] = (long long)smem + 1;
+            }
+            if (active < 1) continue;
+            const long long passes = (items + (long long)C * T - 1) / ((long long)C * T);
+            const long long waves = (B + active - 1) / active;
+            const double cost = (double)waves * (double)passes + 1e-6 * C * T;      // ties -> fewer threads
+            if (cost < best_cost) { best_cost = cost; bestC = C; bestT = T; }
+        }
+    {
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned)(B * C)); lc.blockDim = dim3(BF_REFINE_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+        lc.gridDim = dim3((unsigned)(B * bestC)); lc.blockDim = dim3(bestT); lc.dynamicSmemBytes = smem; lc.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = bestC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        int nclusters = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, bf_refine_kernel, &lc);
-        if ((e != cudaSuccess || nclusters < 1) && C > 1) { cudaGetLastError(); continue; }
-        e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap, max_views, (float*)gscratch);
-        if (e != cudaSuccess) {
-            if (C > 1) { cudaGetLastError(); continue; }
-            return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
-        }
-        h->last_refine_cluster = C;
-        break;
+        cudaError_t e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap, max_views, (float*)gscratch);
+        if (e != cudaSuccess) return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
+        h->last_refine_cluster = bestC * 1000 + bestT;
     }
     return BF_OK;
 }
