@@ -98,25 +98,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_FIELDS = (("tensor_cam", 6), ("R_cam", 9), ("scores", 1), ("pred_boxes", 4), ("pred_proj_xy", 2))
+
+
 def pin_keyframe(kf):
-    """Host (pinned) staging of one keyframe's detections: what the e2e pass copies in every step."""
-    kf._pinned = {k: torch.from_numpy(getattr(kf, k)).pin_memory() for k in
-                  ("tensor_cam", "R_cam", "scores", "pred_boxes", "pred_proj_xy")}
-    return sum(t.numel() * t.element_size() for t in kf._pinned.values()) + 64   # + the 4x4 pose
+    """Host staging of one keyframe's detections in ONE pinned buffer (field after field), so the e2e pass
+    issues a single H2D copy per keyframe."""
+    n = kf.tensor_cam.shape[0]
+    flat = np.concatenate([np.ascontiguousarray(getattr(kf, k), dtype=np.float32).reshape(-1) for k, _ in _FIELDS])
+    kf._pinned = torch.from_numpy(flat).pin_memory()
+    return flat.nbytes + 64   # + the 4x4 pose
+
+
+def split_fields(buf, n):
+    out, o = {}, 0
+    for k, w in _FIELDS:
+        t = buf[o:o + n * w]
+        out[k] = t.view(n, 3, 3) if k == "R_cam" else (t if w == 1 else t.view(n, w))
+        o += n * w
+    return out
 
 
 def make_instances(sess, kf, api, resident):
     """demo.py:216-221 for the CUDA product: detections (pinned host or HBM-resident) -> Instances3D on the GPU."""
     from boxfusion_b200 import ops
     dev = sess.device
-    src = kf._resident if resident else kf._pinned
     n = kf.tensor_cam.shape[0]
     ins = api.Instances3D((kf.image_size[1], kf.image_size[0]))
     if resident:
-        t = {k: v.clone() for k, v in src.items()}
+        t = split_fields(kf._resident.clone(), n)
     else:
-        t = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
-        ops.Profile.h2d_bytes += sum(v.numel() * v.element_size() for v in src.values())
+        t = split_fields(kf._pinned.to(dev, non_blocking=True), n)
+        ops.Profile.h2d_bytes += kf._pinned.numel() * 4
     ins.scores, ins.pred_boxes, ins.pred_proj_xy = t["scores"], t["pred_boxes"], t["pred_proj_xy"]
     ins.pred_boxes_3d = api.GeneralInstance3DBoxes(t["tensor_cam"], t["R_cam"])
     pose_np = np.repeat(kf.pose[None], repeats=n, axis=0)
@@ -142,7 +155,7 @@ def run_ours(args, rank, world, local_rank):
     h2d_per_step = []
     for kf in [k for s in seqs for k in s] + warm:
         h2d_per_step.append(pin_keyframe(kf))
-        kf._resident = {k: v.to(dev) for k, v in kf._pinned.items()}
+        kf._resident = kf._pinned.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def run_pass(frames_by_seq, resident, timing, log):
@@ -162,9 +175,11 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         return [x.elapsed_time(y) for x, y in evs], calls, sess
 
-    # warm-up (untimed): >= 3 steps of another sequence, both passes
+    # warm-up (untimed): >= 3 steps of another sequence through both passes, then the measured sequence once so that
+    # the library's grow-only scratch and torch's caching allocator have reached their steady-state sizes
     run_pass([warm[: max(W, 3) + 8]], True, False, False)
     run_pass([warm[: max(W, 3)]], False, False, False)
+    run_pass(seqs, True, False, False)
     fp32_peak = ops.probe_fp32() if rank == 0 else None
 
     def barrier():

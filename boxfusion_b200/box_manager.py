@@ -46,6 +46,9 @@ class BoxManager:
             self.fusion_flag.append(0)
 
     def add_fusion_ind(self, idx_list):
+        if self._fused_n == len(self.already_fusion):        # keep the lookup set in step with the public list
+            self._fused_set.add(tuple(int(x) for x in idx_list))
+            self._fused_n += 1
         self.already_fusion.append(copy.deepcopy(idx_list))
 
     def check_if_fusion(self, idx_list):

@@ -22,6 +22,13 @@ class GeneralInstance3DBoxes(object):
         self.R = torch.as_tensor(R, dtype=torch.float32, device=device).clone()
 
     @classmethod
+    def _wrap(cls, tensor, R, dof=None):
+        """Adopt freshly produced tensors (results of cat / indexing) without the defensive clone of __init__."""
+        obj = cls.__new__(cls)
+        obj.dof, obj.box_dim, obj.tensor, obj.R = dof, 6 + 3 * 3, tensor, R
+        return obj
+
+    @classmethod
     def empty(cls, dof=None):
         return cls(torch.zeros((0, 6)), torch.zeros((0, 3, 3)), dof=dof)
 
@@ -89,7 +96,9 @@ class GeneralInstance3DBoxes(object):
             return type(self)(self.tensor[item].view(1, -1), self.R[item].view(1, 3, 3), dof=self.dof)
         b, r = self.tensor[item], self.R[item]
         assert b.dim() == 2, f"Indexing on Boxes with {item} failed to return a matrix!"
-        return type(self)(b, r, dof=self.dof)
+        if isinstance(item, slice):
+            return type(self)(b, r, dof=self.dof)              # a slice is a view: clone like the reference
+        return type(self)._wrap(b, r, dof=self.dof)            # advanced indexing already copied
 
     def __len__(self):
         return self.tensor.shape[0]
@@ -103,8 +112,8 @@ class GeneralInstance3DBoxes(object):
         if len(boxes_list) == 0:
             return cls.empty()
         assert all(isinstance(b, cls) for b in boxes_list)
-        return cls(torch.cat([b.tensor for b in boxes_list], dim=0), torch.cat([b.R for b in boxes_list], dim=0),
-                   dof=boxes_list[0].dof)
+        return cls._wrap(torch.cat([b.tensor for b in boxes_list], dim=0), torch.cat([b.R for b in boxes_list], dim=0),
+                         dof=boxes_list[0].dof)
 
     def split(self, split_size_or_sections):
         return [type(self)(t, r, dof=self.dof) for t, r in

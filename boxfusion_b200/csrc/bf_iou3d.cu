@@ -3,9 +3,10 @@
 // Pipeline (all on one stream, no host round trip):
 //   bf_planes_kernel     per box: 12 float64 hull planes + float32 AABB            (N threads)
 //   bf_pairs_kernel      per pair: exact AABB reject -> analytic IoU (ANALYTIC mode, co-axial pairs)
-//                        or containment gate -> append to a work list             (M*N threads)
-//   bf_count_kernel      per gate-passing pair, one warp: 25^3 inside-counts by per-row bisection,
-//                        IoU in float64; writes the dense matrix and/or NMS mask bits (persistent grid)
+//                        or append to a candidate list                             (M*N threads)
+//   bf_count_kernel      per candidate, one CTA: containment gate (40 points over the threads), then the
+//                        25^3 inside-counts by per-row bisection (625 rows over the threads), IoU in
+//                        float64; writes the dense matrix and/or NMS mask bits       (persistent grid)
 //
 // Bound: FP64/FP32 CUDA-core issue, not HBM (inputs are KBs).
 #include "bf_iou3d.cuh"
@@ -13,24 +14,28 @@
 struct bf_work_item { int a, b; };
 
 // ------------------------------------------------------------------------------------------------
+// One thread per (box, face): the two triangle planes of that face; the first thread of a box also writes the AABB.
 __global__ void bf_planes_kernel(const float* __restrict__ corners, int N, double* __restrict__ planes,
                                  float* __restrict__ aabb) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * N) return;
+    const int n = t / 6, f = t - 6 * n;
     float c[24];
 #pragma unroll
     for (int k = 0; k < 24; ++k) c[k] = corners[24 * n + k];
-    double pl[48];
-    bf_hull_planes(c, pl);
+    double pl[8];
+    bf_face_planes(c, f, pl);
 #pragma unroll
-    for (int k = 0; k < 48; ++k) planes[48 * (size_t)n + k] = pl[k];
-    float lo[3] = {c[0], c[1], c[2]}, hi[3] = {c[0], c[1], c[2]};
+    for (int k = 0; k < 8; ++k) planes[48 * (size_t)n + 8 * f + k] = pl[k];
+    if (f == 0) {
+        float lo[3] = {c[0], c[1], c[2]}, hi[3] = {c[0], c[1], c[2]};
 #pragma unroll
-    for (int i = 1; i < 8; ++i)
+        for (int i = 1; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], c[3 * i + k]); hi[k] = fmaxf(hi[k], c[3 * i + k]); }
+            for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], c[3 * i + k]); hi[k] = fmaxf(hi[k], c[3 * i + k]); }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { aabb[6 * n + k] = lo[k]; aabb[6 * n + 3 + k] = hi[k]; }
+        for (int k = 0; k < 3; ++k) { aabb[6 * n + k] = lo[k]; aabb[6 * n + 3 + k] = hi[k]; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,49 +167,61 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
             return;
         }
     }
-    if (!bf_gate(ca, cb, planesA + 48 * (size_t)a, planesB + 48 * (size_t)b)) return;
-    atomicAdd(&counters[3], 1ULL);
-    const unsigned long long slot = atomicAdd(&counters[0], 1ULL);
+    const unsigned long long slot = atomicAdd(&counters[0], 1ULL);      // candidate: gate + counts in bf_count_kernel
     if (slot < (unsigned long long)work_cap) { work[slot].a = a; work[slot].b = b; }
     else atomicExch(&counters[5], 1ULL);
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp per gate-passing pair (persistent, warp-stride over the work list).
-#define BF_COUNT_WARPS 8
-__global__ void __launch_bounds__(BF_COUNT_WARPS * 32)
-bf_count_kernel(const float* __restrict__ aabbA, const double* __restrict__ planesA, const float* __restrict__ aabbB,
-                const double* __restrict__ planesB, int N, const bf_work_item* __restrict__ work, int work_cap,
-                const unsigned long long* __restrict__ counters, double* __restrict__ iou, int32_t* __restrict__ counts,
-                double thr, const int32_t* __restrict__ rank, uint32_t* __restrict__ mask,
-                uint32_t* __restrict__ rowany, int W) {
-    __shared__ double s_pl[BF_COUNT_WARPS][2][48];
-    __shared__ double s_grid[BF_COUNT_WARPS][3][BF_NS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One CTA per candidate pair (persistent, CTA-stride over the work list): gate, then counts.
+#define BF_COUNT_THREADS 128
+__global__ void __launch_bounds__(BF_COUNT_THREADS)
+bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA, const double* __restrict__ planesA,
+                const float* __restrict__ cornersB, const float* __restrict__ aabbB, const double* __restrict__ planesB,
+                int N, const bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
+                double* __restrict__ iou, int32_t* __restrict__ counts, double thr, const int32_t* __restrict__ rank,
+                uint32_t* __restrict__ mask, uint32_t* __restrict__ rowany, int W) {
+    __shared__ double s_pl[2][48];
+    __shared__ double s_grid[3][BF_NS];
+    __shared__ float s_c[2][24];
+    __shared__ int s_red[3][BF_COUNT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long nwork = counters[0];
     if (nwork > (unsigned long long)work_cap) nwork = work_cap;
-    const int gwarp = blockIdx.x * BF_COUNT_WARPS + warp, nwarps = gridDim.x * BF_COUNT_WARPS;
-    for (unsigned long long w = gwarp; w < nwork; w += nwarps) {
+    for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int a = work[w].a, b = work[w].b;
-        __syncwarp();
-        for (int k = lane; k < 48; k += 32) {
-            s_pl[warp][0][k] = planesA[48 * (size_t)a + k];
-            s_pl[warp][1][k] = planesB[48 * (size_t)b + k];
+        __syncthreads();
+        if (tid < 48) { s_pl[0][tid] = planesA[48 * (size_t)a + tid]; s_pl[1][tid] = planesB[48 * (size_t)b + tid]; }
+        if (tid >= 64 && tid < 88) { s_c[0][tid - 64] = cornersA[24 * (size_t)a + tid - 64]; s_c[1][tid - 64] = cornersB[24 * (size_t)b + tid - 64]; }
+        if (tid >= 96 && tid < 96 + 3) {
+            const int ax = tid - 96;
+            const float lo = fminf(aabbA[6 * a + ax], aabbB[6 * b + ax]), hi = fmaxf(aabbA[6 * a + 3 + ax], aabbB[6 * b + 3 + ax]);   // instances.py:581-582
+            for (int i = 0; i < BF_NS; ++i) s_grid[ax][i] = (double)bf_linspace25(lo, hi, i);
         }
-        const float* ba = aabbA + 6 * a;
-        const float* bb = aabbB + 6 * b;
-        for (int k = lane; k < 3 * BF_NS; k += 32) {
-            const int ax = k / BF_NS, i = k % BF_NS;
-            const float lo = fminf(ba[ax], bb[ax]), hi = fmaxf(ba[3 + ax], bb[3 + ax]);   // instances.py:581-582
-            s_grid[warp][ax][i] = (double)bf_linspace25(lo, hi, i);
+        __syncthreads();
+        // ---- containment gate (instances.py:514-557): 2 x 20 points, one per thread -------------------------
+        int inside = 0;
+        if (tid < 40) {
+            const int which = tid / 20, k = tid - 20 * which;          // points of box `which` against the other hull
+            const float* c = s_c[which];
+            float px, py, pz;
+            if (k < 8) { px = c[3 * k]; py = c[3 * k + 1]; pz = c[3 * k + 2]; }
+            else {
+                const int i0 = c_bf_edges[k - 8][0], i1 = c_bf_edges[k - 8][1];
+                px = __fadd_rn(c[3 * i0], c[3 * i1]) * 0.5f; py = __fadd_rn(c[3 * i0 + 1], c[3 * i1 + 1]) * 0.5f;
+                pz = __fadd_rn(c[3 * i0 + 2], c[3 * i1 + 2]) * 0.5f;
+            }
+            inside = bf_inside12(s_pl[1 - which], px, py, pz) ? 1 : 0;
         }
-        __syncwarp();
+        if (!__syncthreads_or(inside)) continue;                        // gate failed: IoU stays 0
+        if (tid == 0) atomicAdd(&counters[3], 1ULL);
+        // ---- 25^3 counts: 625 rows over the threads ---------------------------------------------------------
         int n1 = 0, n2 = 0, n12 = 0;
-        for (int r = lane; r < BF_NS * BF_NS; r += 32) {
-            const double y = s_grid[warp][1][r / BF_NS], z = s_grid[warp][2][r % BF_NS];
+        for (int r = tid; r < BF_NS * BF_NS; r += BF_COUNT_THREADS) {
+            const double y = s_grid[1][r / BF_NS], z = s_grid[2][r % BF_NS];
             int lo1, hi1, lo2, hi2;
-            bf_row_interval(s_pl[warp][0], s_grid[warp][0], y, z, lo1, hi1);
-            bf_row_interval(s_pl[warp][1], s_grid[warp][0], y, z, lo2, hi2);
+            bf_row_interval(s_pl[0], s_grid[0], y, z, lo1, hi1);
+            bf_row_interval(s_pl[1], s_grid[0], y, z, lo2, hi2);
             const int c1 = max(0, hi1 - lo1 + 1), c2 = max(0, hi2 - lo2 + 1);
             n1 += c1; n2 += c2;
             if (c1 > 0 && c2 > 0) n12 += max(0, min(hi1, hi2) - max(lo1, lo2) + 1);
@@ -215,7 +232,11 @@ bf_count_kernel(const float* __restrict__ aabbA, const double* __restrict__ plan
             n2 += __shfl_xor_sync(0xffffffffu, n2, o);
             n12 += __shfl_xor_sync(0xffffffffu, n12, o);
         }
-        if (lane == 0) {
+        if (lane == 0) { s_red[0][warp] = n1; s_red[1][warp] = n2; s_red[2][warp] = n12; }
+        __syncthreads();
+        if (tid == 0) {
+            n1 = n2 = n12 = 0;
+            for (int k = 0; k < BF_COUNT_THREADS / 32; ++k) { n1 += s_red[0][k]; n2 += s_red[1][k]; n12 += s_red[2][k]; }
             const double v = (double)n12 / ((double)(n1 + n2 - n12) + 1e-6);                  // instances.py:608
             const size_t p = (size_t)a * N + b;
             if (iou) iou[p] = v;
@@ -241,13 +262,13 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* corner
     void* p;
     if ((rc = bf_scratch(h, BF_SCRATCH_PLANES_A, sizeof(double) * 48 * (size_t)M, &p))) return rc; plA = (double*)p;
     if ((rc = bf_scratch(h, BF_SCRATCH_AABB_A, sizeof(float) * 6 * (size_t)M, &p))) return rc; bbA = (float*)p;
-    bf_planes_kernel<<<bf_blocks(M, 64), 64, 0, st>>>(cornersA, M, plA, bbA);
+    bf_planes_kernel<<<bf_blocks(6LL * M, 96), 96, 0, st>>>(cornersA, M, plA, bbA);
     BF_LAUNCH_CHECK(h, "bf_planes_kernel");
     if (cornersB == cornersA && N == M) { plB = plA; bbB = bbA; }
     else {
         if ((rc = bf_scratch(h, BF_SCRATCH_PLANES_B, sizeof(double) * 48 * (size_t)N, &p))) return rc; plB = (double*)p;
         if ((rc = bf_scratch(h, BF_SCRATCH_AABB_B, sizeof(float) * 6 * (size_t)N, &p))) return rc; bbB = (float*)p;
-        bf_planes_kernel<<<bf_blocks(N, 64), 64, 0, st>>>(cornersB, N, plB, bbB);
+        bf_planes_kernel<<<bf_blocks(6LL * N, 96), 96, 0, st>>>(cornersB, N, plB, bbB);
         BF_LAUNCH_CHECK(h, "bf_planes_kernel");
     }
     const long long total = (long long)M * N;
@@ -263,9 +284,9 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* corner
     bf_pairs_kernel<<<bf_blocks(total, 128), 128, 0, st>>>(cornersA, bbA, plA, M, cornersB, bbB, plB, N, triangle, mode,
                                                            iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, W);
     BF_LAUNCH_CHECK(h, "bf_pairs_kernel");
-    const int grid = h->sm_count * 4;
-    bf_count_kernel<<<grid, BF_COUNT_WARPS * 32, 0, st>>>(bbA, plA, bbB, plB, N, work, (int)cap, counters, iou, counts,
-                                                          thr, rank, mask, rowany, W);
+    const int grid = h->sm_count * 8;
+    bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, N, work, (int)cap, counters,
+                                                       iou, counts, thr, rank, mask, rowany, W);
     BF_LAUNCH_CHECK(h, "bf_count_kernel");
     if (stats)   // pairs, AABB-passing, gate-passing, analytic
         BF_CUDA(h, cudaMemcpyAsync(stats, counters + 1, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));

@@ -3,7 +3,7 @@
 //
 // SAMPLED_REF.  The reference takes its half-spaces from Qhull.  For the 8 float32 corners of a
 // box the convex hull is unique: each face is folded along its convex diagonal into two triangles
-// and Qhull reports one unit-normal plane per triangle.  bf_hull_planes() rebuilds those 12 planes
+// and Qhull reports one unit-normal plane per triangle.  bf_face_planes() rebuilds those 12 planes
 // in float64 from the float32 corners (agreement with scipy <= 1e-14, tests/test_oracle_golden.py),
 // so the 25^3 inside-counts are the reference's.
 //
@@ -37,8 +37,8 @@ __device__ __forceinline__ void bf_plane3(const double* p0, const double* p1, co
     out[0] = nx; out[1] = ny; out[2] = nz; out[3] = d;
 }
 
-// 12 outward half-spaces n.p + d <= 0 of hull(8 float32 corners); planes[12][4].
-__device__ inline void bf_hull_planes(const float* __restrict__ c24, double* __restrict__ planes) {
+// The two outward half-spaces n.p + d <= 0 of face f of hull(8 float32 corners); planes[2][4].
+__device__ inline void bf_face_planes(const float* __restrict__ c24, int f, double* __restrict__ planes) {
     double c[8][3], cen[3] = {0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -46,19 +46,17 @@ __device__ inline void bf_hull_planes(const float* __restrict__ c24, double* __r
         for (int k = 0; k < 3; ++k) { c[i][k] = (double)c24[3 * i + k]; cen[k] = __dadd_rn(cen[k], c[i][k]); }
 #pragma unroll
     for (int k = 0; k < 3; ++k) cen[k] = cen[k] * 0.125;
-    for (int f = 0; f < 6; ++f) {
-        const double *a = c[c_bf_faces[f][0]], *b = c[c_bf_faces[f][1]], *cc = c[c_bf_faces[f][2]], *d = c[c_bf_faces[f][3]];
-        double P[4];
-        bf_plane3(a, b, cc, cen, P);
-        const double s = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[0], d[0]), __dmul_rn(P[1], d[1])), __dmul_rn(P[2], d[2])), P[3]);
-        if (s <= 0) {
+    const double *a = c[c_bf_faces[f][0]], *b = c[c_bf_faces[f][1]], *cc = c[c_bf_faces[f][2]], *d = c[c_bf_faces[f][3]];
+    double P[4];
+    bf_plane3(a, b, cc, cen, P);
+    const double s = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[0], d[0]), __dmul_rn(P[1], d[1])), __dmul_rn(P[2], d[2])), P[3]);
+    if (s <= 0) {                                          // d below abc: the face folds along a-c
 #pragma unroll
-            for (int k = 0; k < 4; ++k) planes[(2 * f) * 4 + k] = P[k];
-            bf_plane3(a, cc, d, cen, planes + (2 * f + 1) * 4);
-        } else {
-            bf_plane3(a, b, d, cen, planes + (2 * f) * 4);
-            bf_plane3(b, cc, d, cen, planes + (2 * f + 1) * 4);
-        }
+        for (int k = 0; k < 4; ++k) planes[k] = P[k];
+        bf_plane3(a, cc, d, cen, planes + 4);
+    } else {                                               // folds along b-d
+        bf_plane3(a, b, d, cen, planes);
+        bf_plane3(b, cc, d, cen, planes + 4);
     }
 }
 
@@ -69,26 +67,6 @@ __device__ __forceinline__ bool bf_inside12(const double* __restrict__ pl, doubl
         if (!(v <= BF_INSIDE_EPS)) return false;
     }
     return true;
-}
-
-// check_intersection (instances.py:514-557): any of the 8 corners + 12 float32 edge midpoints of one
-// box inside the other hull (<= 1e-6), either way round.
-__device__ inline bool bf_gate(const float* __restrict__ ca, const float* __restrict__ cb,
-                               const double* __restrict__ pla, const double* __restrict__ plb) {
-    for (int i = 0; i < 8; ++i) {
-        if (bf_inside12(plb, ca[3 * i], ca[3 * i + 1], ca[3 * i + 2])) return true;
-        if (bf_inside12(pla, cb[3 * i], cb[3 * i + 1], cb[3 * i + 2])) return true;
-    }
-    for (int e = 0; e < 12; ++e) {
-        const int i0 = c_bf_edges[e][0], i1 = c_bf_edges[e][1];
-        const float ax = __fadd_rn(ca[3 * i0], ca[3 * i1]) * 0.5f, ay = __fadd_rn(ca[3 * i0 + 1], ca[3 * i1 + 1]) * 0.5f,
-                    az = __fadd_rn(ca[3 * i0 + 2], ca[3 * i1 + 2]) * 0.5f;
-        if (bf_inside12(plb, ax, ay, az)) return true;
-        const float bx = __fadd_rn(cb[3 * i0], cb[3 * i1]) * 0.5f, by = __fadd_rn(cb[3 * i0 + 1], cb[3 * i1 + 1]) * 0.5f,
-                    bz = __fadd_rn(cb[3 * i0 + 2], cb[3 * i1 + 2]) * 0.5f;
-        if (bf_inside12(pla, bx, by, bz)) return true;
-    }
-    return false;
 }
 
 // np.linspace(float32 lo, float32 hi, 25) under NumPy 2 (float32): x_i = fl(fl(i*step)+lo), x_24 = hi.

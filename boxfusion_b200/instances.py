@@ -68,11 +68,20 @@ def _nms_device(instance_lists, box_manager, corners, centers, scores, init_id, 
     fl, ln, flag = packed[: n * cap].view(n, cap), packed[n * cap: n * cap + n], packed[n * cap + n:]
     keep, success, status = ops.nms3d(corners, centers, order, iid, poses, fl, ln, flag, float(iou_threshold),
                                       float(box_manager.translation_gap), float(box_manager.rotation_gap), 0.5, IOU_MODE)
-    out = ops.to_host(torch.cat([packed, keep, success, status]))                   # the call's single D2H
+    # the call's single D2H also carries what correspondence_association needs on the host right afterwards
+    # (largest box dimension, scores, init ids) so that it does not have to synchronise again
+    dims = instance_lists.get("pred_boxes_3d").tensor[:, 3:6] if instance_lists.has("pred_boxes_3d") else None
+    extra = None
+    if dims is not None and dims.is_cuda:
+        extra = torch.cat([torch.amax(dims, dim=1), s]).view(torch.int32)
+    out = ops.to_host(torch.cat([packed, keep, success, status] + ([extra] if extra is not None else [])))
+    if extra is not None:
+        tail = out[n * cap + 4 * n + 1:].view(np.float32)
+        instance_lists._bf_host = {"max_dim": tail[:n].copy(), "scores": tail[n:2 * n].copy(), "n": n}
     fl_o = out[: n * cap].reshape(n, cap)
     ln_o, flag_o = out[n * cap: n * cap + n], out[n * cap + n: n * cap + 2 * n]
     keep_o, succ_o = out[n * cap + 2 * n: n * cap + 3 * n], out[n * cap + 3 * n: n * cap + 4 * n]
-    if out[-1] != 0:
+    if out[n * cap + 4 * n] != 0:
         raise RuntimeError(f"bf_nms3d: a fusion list exceeded the device capacity ({cap})")
     box_manager.apply_lists(fl_o, ln_o, flag_o, ln_h)
     keep_idx, succ_idx = np.nonzero(keep_o)[0], np.nonzero(succ_o)[0]
@@ -143,12 +152,22 @@ class Instances3D:
                 raise IndexError("Instances3D index out of range!")
             item = slice(item, None, len(self))
         ret = Instances3D(image_size=self.image_size)
+        dev_item = {}                       # integer index arrays are uploaded once per device, not once per field
+
+        def on(v):
+            t = v.tensor if hasattr(v, "tensor") else v
+            if not (isinstance(item, np.ndarray) and item.dtype.kind in "iu" and isinstance(t, torch.Tensor) and t.is_cuda):
+                return item
+            if t.device not in dev_item:
+                dev_item[t.device] = torch.from_numpy(np.ascontiguousarray(item, dtype=np.int64)).to(t.device, non_blocking=True)
+            return dev_item[t.device]
+
         for k, v in self._fields.items():
             if isinstance(v, (torch.Tensor, np.ndarray)) or hasattr(v, "tensor"):
                 if isinstance(v, np.ndarray) and isinstance(item, torch.Tensor):
                     ret.set(k, v[item.cpu().numpy()])
                 else:
-                    ret.set(k, v[item])
+                    ret.set(k, v[on(v)])
             elif hasattr(v, "__iter__"):
                 if isinstance(item, np.ndarray) and item.dtype == np.bool_:
                     ret.set(k, [x for i, x in enumerate(v) if item[i]])
@@ -223,7 +242,12 @@ class Instances3D:
         cam_pose = self.cam_pose
         dev = ops._pick_device(boxes.tensor)
         corners = ops.box_corners(boxes.tensor, boxes.R)
-        pose_inv = torch.linalg.inv(cam_pose)                 # same call as the reference (:350), on cam_pose's device
+        # same call as the reference (:350), on cam_pose's device; a keyframe's detections share one pose, which is
+        # then inverted once (batched LU treats every matrix independently, so the values are identical)
+        if cam_pose.shape[0] > 1 and bool((cam_pose == cam_pose[:1]).all()):
+            pose_inv = torch.linalg.inv(cam_pose[:1]).expand(cam_pose.shape[0], 4, 4)
+        else:
+            pose_inv = torch.linalg.inv(cam_pose)
         K = _as_numpy(K)
         uv = ops.project_boxes(corners, pose_inv.to(dev), K, float(W), float(H))
         self.projected_boxes = uv if boxes.tensor.is_cuda else uv.to(boxes.tensor.device)
@@ -247,10 +271,14 @@ class Instances3D:
         N_glo = len(global_pred_box)
         keep_idx = copy.deepcopy(np.asarray(mask))
         small_size = cfg["box_fusion"]["small_size"]
-        pred_size = _as_numpy(pred_instances.get("pred_boxes_3d").dims)
+        host = getattr(all_pred_box, "_bf_host", None)       # left by spatial_association's download, if any
+        if host is not None and host["n"] == len(all_pred_box):
+            pred_max = host["max_dim"][N_glo:]
+        else:
+            host = None
+            pred_max = np.max(_as_numpy(pred_instances.get("pred_boxes_3d").dims)[:, :3], axis=1)
         success = set(int(i) for i in cur_success_nms)
-        small_idx = [int(i) for i in cur_keep_idx
-                     if not (np.max(pred_size[i, :3]) > small_size or int(i) in success)]
+        small_idx = [int(i) for i in cur_keep_idx if not (pred_max[i] > small_size or int(i) in success)]
         glo_keep = keep_idx[keep_idx < N_glo]
         if len(small_idx) > 0 and len(glo_keep) > 0:
             gb = global_pred_box.get("pred_boxes_3d")
@@ -264,8 +292,11 @@ class Instances3D:
             best, best_iou = ops.corr2d(corners, small_mask, pose_inv.astype(np.float32), _as_numpy(intrinsic),
                                         float(W), float(H), det)
             best, best_iou = ops.to_host(best), ops.to_host(best_iou)
-            cur_scores = _as_numpy(pred_instances.scores)
-            glo_scores = _as_numpy(global_pred_box.scores)
+            if host is not None:
+                glo_scores, cur_scores = host["scores"][:N_glo], host["scores"][N_glo:]
+            else:
+                cur_scores = _as_numpy(pred_instances.scores)
+                glo_scores = _as_numpy(global_pred_box.scores)
             init_id = _as_numpy(all_pred_box.init_id)
             for k, idx in enumerate(small_idx):                                                  # sequential tail (:463-483)
                 if not (best_iou[k] > threshold):
