@@ -6,7 +6,7 @@
 
 int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* cornersB, int N, int triangle, int mode,
                  double* iou, int32_t* counts, int64_t* stats, double thr, const int32_t* rank, uint32_t* mask,
-                 uint32_t* rowany, int W, cudaStream_t st);
+                 uint32_t* rowany, int W, unsigned long long* edges, int edge_cap, cudaStream_t st);
 int bf_iou3d_overflowed(bf_handle* h, cudaStream_t st, int* overflow);
 
 __global__ void bf_rank_kernel(const int32_t* __restrict__ order, int N, int32_t* __restrict__ rank) {
@@ -36,7 +36,120 @@ __device__ __forceinline__ void bf_sorted_insert(int32_t* list, int& len, int32_
     ++len;
 }
 
-// One warp.  Walks, in ascending score rank, the heads that have at least one over-threshold partner;
+// BoxManager.record for one suppressed box `idx` of head `cur` (box_manager.py:48-86).  lc/len_c: the head's list.
+struct bf_record_ctx {
+    const int32_t* order; const int32_t* init_id; const float* poses; const float* centers;
+    int32_t* fl; int32_t* flen; int32_t* fflag; int32_t* keep; int32_t* status;
+    float translation_gap, rotation_gap, center_gap;
+};
+
+__device__ __forceinline__ void bf_record_one(const bf_record_ctx& c, int cur, int idx, int32_t* lc, int& len_c,
+                                              bool& cur_in_keep) {
+    const float* cc = c.centers + 3 * cur;
+    const float* ci = c.centers + 3 * idx;
+    const float ex = cc[0] - ci[0], ey = cc[1] - ci[1], ez = cc[2] - ci[2];
+    const float cdis = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+    const int len_i = c.flen[idx];
+    const int32_t* li = c.fl + (size_t)idx * BF_FUSION_CAP;
+    if (len_i == 1) {                                     // box_manager.py:50-62
+        const float* pi = c.poses + 16 * (size_t)c.init_id[idx];
+        int cnt = 0;
+        for (int k = 0; k < len_c; ++k)
+            cnt += bf_views_differ(c.poses + 16 * (size_t)lc[k], pi, c.translation_gap, c.rotation_gap, true, cdis, c.center_gap);
+        if (cnt == len_c && len_c < 5) {
+            if (len_c + 1 > BF_FUSION_CAP) c.status[0] = BF_ERR_CAPACITY;
+            else bf_sorted_insert(lc, len_c, c.init_id[idx]);
+        }
+    } else {                                              // box_manager.py:65-86
+        const float* pc = c.poses + 16 * (size_t)c.init_id[cur];
+        int cnt = 0;
+        for (int k = 0; k < len_i; ++k)
+            cnt += bf_views_differ(c.poses + 16 * (size_t)li[k], pc, c.translation_gap, c.rotation_gap, true, cdis, c.center_gap);
+        if (cnt == len_i && len_i < 5) {
+            if (len_c + len_i > BF_FUSION_CAP) c.status[0] = BF_ERR_CAPACITY;
+            else for (int k = 0; k < len_i; ++k) bf_sorted_insert(lc, len_c, li[k]);
+        } else if (cur_in_keep) {                         // swap: keep.remove(cur); keep.append(idx)
+            cur_in_keep = false;
+            c.keep[idx] = 1;                              // forced keep
+            c.keep[cur] = -1;                             // dropped
+        }
+        if (c.fflag[idx] == 1) c.fflag[cur] = 1;
+    }
+}
+
+// Sparse greedy matching (the common case: few over-threshold pairs).  The IoU kernels emit one edge
+// (rank_lo << 32 | rank_hi) per over-threshold pair.  One CTA sorts the edges, thread 0 walks them in order to
+// decide which (head, partner) pairs are live - nms_3d's loop (instances.py:58-97) touches nothing else - and then
+// record() runs in parallel over heads: calls of different heads write disjoint lists/flags and only read lists of
+// suppressed boxes, which never change.  Falls through (returns) when the edge list overflowed; the dense kernel
+// below handles that case.
+#define BF_EDGE_CAP 8192
+__global__ void __launch_bounds__(1024)
+bf_greedy_edges_kernel(const unsigned long long* __restrict__ edges, const unsigned long long* __restrict__ counters,
+                       int N, int W, bf_record_ctx ctx, int32_t* __restrict__ success) {
+    extern __shared__ unsigned long long s_keys[];
+    const unsigned long long E64 = counters[6];
+    if (E64 > BF_EDGE_CAP) return;
+    const int E = (int)E64, tid = threadIdx.x, T = blockDim.x;
+    int n2 = 1;
+    while (n2 < E) n2 <<= 1;
+    uint32_t* remaining = (uint32_t*)(s_keys + n2);
+    unsigned char* act = (unsigned char*)(remaining + W);
+    for (int i = tid; i < N; i += T) { ctx.keep[i] = 0; success[i] = 0; }
+    if (tid == 0) ctx.status[0] = 0;
+    for (int i = tid; i < n2; i += T) s_keys[i] = (i < E) ? edges[i] : ~0ULL;
+    for (int w = tid; w < W; w += T) {
+        const int base = w << 5;
+        remaining[w] = (base + 32 <= N) ? 0xffffffffu : ((base < N) ? ((1u << (N - base)) - 1u) : 0u);
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)                      // bitonic sort, ascending
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += T) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long a = s_keys[i], b = s_keys[p];
+                    if (((i & k) == 0) ? (a > b) : (a < b)) { s_keys[i] = b; s_keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (tid == 0) {                                        // the serial part of nms_3d: who is a head, who is suppressed
+        int cur = -1;
+        bool alive = false;
+        for (int e = 0; e < E; ++e) {
+            const int r0 = (int)(s_keys[e] >> 32), r1 = (int)(s_keys[e] & 0xffffffffu);
+            if (r0 != cur) { cur = r0; alive = (remaining[r0 >> 5] >> (r0 & 31)) & 1u; }
+            const bool live = alive && ((remaining[r1 >> 5] >> (r1 & 31)) & 1u);
+            act[e] = live ? 1 : 0;
+            if (live) remaining[r1 >> 5] &= ~(1u << (r1 & 31));
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += T) {                     // one thread per head: record() over its live partners, in order
+        const int r0 = (int)(s_keys[e] >> 32);
+        if (e > 0 && (int)(s_keys[e - 1] >> 32) == r0) continue;
+        const int cur = ctx.order[r0];
+        int32_t* lc = ctx.fl + (size_t)cur * BF_FUSION_CAP;
+        int len_c = ctx.flen[cur];
+        bool cur_in_keep = true, any = false;
+        for (int g = e; g < E && (int)(s_keys[g] >> 32) == r0; ++g) {
+            if (!act[g]) continue;
+            any = true;
+            bf_record_one(ctx, cur, ctx.order[(int)(s_keys[g] & 0xffffffffu)], lc, len_c, cur_in_keep);
+        }
+        if (any) { success[cur] = 1; ctx.flen[cur] = len_c; }
+    }
+    __syncthreads();
+    for (int r = tid; r < N; r += T) {                     // keep = never suppressed, minus dropped heads, plus forced keeps
+        const int i = ctx.order[r];
+        const bool rem = (remaining[r >> 5] >> (r & 31)) & 1u;
+        const int k = ctx.keep[i];
+        ctx.keep[i] = (k == 1) ? 1 : ((k == -1) ? 0 : (rem ? 1 : 0));
+    }
+}
+
+// Dense fallback (edge list overflowed).  One warp.  Walks, in ascending score rank, the heads that have at least one over-threshold partner;
 // every other box is kept untouched.  Lane 0 performs record(); the other lanes help with the bit-mask rows.
 __global__ void __launch_bounds__(32)
 bf_greedy_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ rowany, int N, int W,
@@ -44,8 +157,10 @@ bf_greedy_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__
                  const float* __restrict__ poses, int M, const float* __restrict__ centers,
                  int32_t* __restrict__ fl, int32_t* __restrict__ flen, int32_t* __restrict__ fflag,
                  float translation_gap, float rotation_gap, float center_gap,
-                 int32_t* __restrict__ keep, int32_t* __restrict__ success, int32_t* __restrict__ status) {
+                 int32_t* __restrict__ keep, int32_t* __restrict__ success, int32_t* __restrict__ status,
+                 const unsigned long long* __restrict__ counters) {
     extern __shared__ uint32_t s_mem[];
+    if (counters[6] <= BF_EDGE_CAP) return;              // bf_greedy_edges_kernel handled this call
     uint32_t* remaining = s_mem;            // [W] ranks not yet suppressed
     uint32_t* sup = s_mem + W;              // [W] scratch: suppressed by the current head
     const int lane = threadIdx.x;
@@ -152,12 +267,14 @@ extern "C" int bf_nms3d(bf_handle* h, const float* corners, const float* centers
     uint32_t* rowany = mask + (size_t)N * W;
     if ((rc = bf_scratch(h, BF_SCRATCH_RANK, sizeof(int32_t) * (size_t)N, &p))) return rc;
     int32_t* rank = (int32_t*)p;
+    if ((rc = bf_scratch(h, BF_SCRATCH_EDGES, sizeof(unsigned long long) * BF_EDGE_CAP, &p))) return rc;
+    unsigned long long* edges = (unsigned long long*)p;
     for (int attempt = 0; attempt < 2; ++attempt) {
         BF_CUDA(h, cudaMemsetAsync(mask, 0, sizeof(uint32_t) * ((size_t)N * W + W), st));
         bf_rank_kernel<<<bf_blocks(N, 128), 128, 0, st>>>(order, N, rank);
         BF_LAUNCH_CHECK(h, "bf_rank_kernel");
         if ((rc = bf_iou3d_run(h, corners, N, corners, N, 1, mode, nullptr, nullptr, nullptr, iou_threshold, rank, mask,
-                               rowany, W, st)))
+                               rowany, W, edges, BF_EDGE_CAP, st)))
             return rc;
         if ((long long)N * N <= (long long)(h->cap[BF_SCRATCH_WORK] / 8)) break;
         int ovf = 0;
@@ -166,11 +283,23 @@ extern "C" int bf_nms3d(bf_handle* h, const float* corners, const float* centers
         if (attempt == 1) return bf_fail(h, BF_ERR_CAPACITY, "bf_nms3d", "work list overflow");
         if ((rc = bf_scratch(h, BF_SCRATCH_WORK, 8 * (size_t)N * N / 2, &p))) return rc;
     }
+    const unsigned long long* counters = (const unsigned long long*)h->buf[BF_SCRATCH_COUNTERS];
+    bf_record_ctx ctx;
+    ctx.order = order; ctx.init_id = init_id; ctx.poses = poses; ctx.centers = centers; ctx.fl = fusion_list;
+    ctx.flen = fusion_len; ctx.fflag = fusion_flag; ctx.keep = keep; ctx.status = status;
+    ctx.translation_gap = translation_gap; ctx.rotation_gap = rotation_gap_deg; ctx.center_gap = center_gap;
+    // sparse path: sorted edge list in shared memory (keys + remaining bit set + live flags)
+    const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
+    BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    bf_greedy_edges_kernel<<<1, 1024, smem_e, st>>>(edges, counters, N, W, ctx, success);
+    BF_LAUNCH_CHECK(h, "bf_greedy_edges_kernel");
+    // dense fallback: returns immediately unless the edge list overflowed
     const size_t smem = sizeof(uint32_t) * 2 * (size_t)W;
     if (smem > 48 * 1024)
         BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bf_greedy_kernel<<<1, 32, smem, st>>>(mask, rowany, N, W, order, init_id, poses, M, centers, fusion_list, fusion_len,
-                                          fusion_flag, translation_gap, rotation_gap_deg, center_gap, keep, success, status);
+                                          fusion_flag, translation_gap, rotation_gap_deg, center_gap, keep, success, status,
+                                          counters);
     BF_LAUNCH_CHECK(h, "bf_greedy_kernel");
     return BF_OK;
 }

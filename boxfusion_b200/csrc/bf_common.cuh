@@ -19,6 +19,7 @@ enum {
     BF_SCRATCH_IOU,           // double per work item
     BF_SCRATCH_MISC,
     BF_SCRATCH_REFINE,        // refine fitness / contributions
+    BF_SCRATCH_EDGES,         // uint64 over-threshold edges (rank_lo << 32 | rank_hi) of bf_nms3d
     BF_SCRATCH_SLOTS
 };
 

@@ -126,7 +126,7 @@ __device__ inline bool bf_analytic_iou(const float* __restrict__ ca, const float
 // ------------------------------------------------------------------------------------------------
 // One thread per pair.  triangle != 0: A and B are the same set and only a < b is evaluated (NMS).
 // Outputs: dense iou/counts zero-filled (when given), work list of gate-passing pairs, stats.
-// counters: [0] work items, [1] pairs, [2] AABB-passing, [3] gate-passing, [4] analytic, [5] overflow
+// counters: [0] work items, [1] pairs, [2] AABB-passing, [3] gate-passing, [4] analytic, [5] overflow, [6] NMS edges
 __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA,
                                 const double* __restrict__ planesA, int M, const float* __restrict__ cornersB,
                                 const float* __restrict__ aabbB, const double* __restrict__ planesB, int N,
@@ -134,7 +134,7 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
                                 bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
                                 // NMS outputs (ANALYTIC hits are thresholded here)
                                 double thr, const int32_t* __restrict__ rank, uint32_t* __restrict__ mask,
-                                uint32_t* __restrict__ rowany, int W) {
+                                uint32_t* __restrict__ rowany, int W, unsigned long long* __restrict__ edges, int edge_cap) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)M * N;
     if (p >= total) return;
@@ -163,6 +163,8 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
                 const int r0 = min(ra, rb), r1 = max(ra, rb);
                 atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
                 atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
+                const unsigned long long e = atomicAdd(&counters[6], 1ULL);
+                if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
             }
             return;
         }
@@ -180,7 +182,8 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
                 const float* __restrict__ cornersB, const float* __restrict__ aabbB, const double* __restrict__ planesB,
                 int N, const bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
                 double* __restrict__ iou, int32_t* __restrict__ counts, double thr, const int32_t* __restrict__ rank,
-                uint32_t* __restrict__ mask, uint32_t* __restrict__ rowany, int W) {
+                uint32_t* __restrict__ mask, uint32_t* __restrict__ rowany, int W, unsigned long long* __restrict__ edges,
+                int edge_cap) {
     __shared__ double s_pl[2][48];
     __shared__ double s_grid[3][BF_NS];
     __shared__ float s_c[2][24];
@@ -246,6 +249,8 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
                 const int r0 = min(ra, rb), r1 = max(ra, rb);
                 atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
                 atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
+                const unsigned long long e = atomicAdd(&counters[6], 1ULL);
+                if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
             }
         }
     }
@@ -255,7 +260,7 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
 // Host driver shared by bf_iou3d_matrix and bf_nms3d.
 int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* cornersB, int N, int triangle, int mode,
                  double* iou, int32_t* counts, int64_t* stats, double thr, const int32_t* rank, uint32_t* mask,
-                 uint32_t* rowany, int W, cudaStream_t st) {
+                 uint32_t* rowany, int W, unsigned long long* edges, int edge_cap, cudaStream_t st) {
     double *plA = nullptr, *plB = nullptr;
     float *bbA = nullptr, *bbB = nullptr;
     int rc;
@@ -282,11 +287,11 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* corner
     unsigned long long* counters = (unsigned long long*)p;
     BF_CUDA(h, cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 8, st));
     bf_pairs_kernel<<<bf_blocks(total, 128), 128, 0, st>>>(cornersA, bbA, plA, M, cornersB, bbB, plB, N, triangle, mode,
-                                                           iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, W);
+                                                           iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, W, edges, edge_cap);
     BF_LAUNCH_CHECK(h, "bf_pairs_kernel");
     const int grid = h->sm_count * 8;
     bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, N, work, (int)cap, counters,
-                                                       iou, counts, thr, rank, mask, rowany, W);
+                                                       iou, counts, thr, rank, mask, rowany, W, edges, edge_cap);
     BF_LAUNCH_CHECK(h, "bf_count_kernel");
     if (stats)   // pairs, AABB-passing, gate-passing, analytic
         BF_CUDA(h, cudaMemcpyAsync(stats, counters + 1, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
@@ -312,7 +317,7 @@ extern "C" int bf_iou3d_matrix(bf_handle* h, const float* cornersA, int M, const
     cudaStream_t st = (cudaStream_t)stream;
     for (int attempt = 0; attempt < 2; ++attempt) {
         int rc = bf_iou3d_run(h, cornersA, M, cornersB, N, 0, mode, iou, counts, stats, 0.0, nullptr,
-                              nullptr, nullptr, 0, st);
+                              nullptr, nullptr, 0, nullptr, 0, st);
         if (rc) return rc;
         if ((long long)M * N <= (long long)(h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item))) break;   // cannot overflow
         int ovf = 0;

@@ -167,6 +167,24 @@ def test_nms_matches_port(n_map, n_det, seed, monkeypatch):
     assert len(ref[1]) > 10 and any(len(l) > 2 for l in ref[2])
 
 
+def test_nms_dense_fallback_when_edge_list_overflows(monkeypatch):
+    """> 8192 over-threshold pairs (a pile of near-identical boxes) take the dense bit-mask kernel."""
+    monkeypatch.setattr(port, "IOU_BACKEND", "c")
+    rs = np.random.RandomState(0)
+    n = 140                                                         # 9730 pairs, all overlapping
+    t = np.tile(np.array([[0.3, -0.2, 0.9, 0.8, 0.6, 0.7]], np.float32), (n, 1))
+    t[:, :3] += rs.normal(0, 0.02, (n, 3)).astype(np.float32)
+    R = np.tile(np.eye(3, dtype=np.float32), (n, 1, 1))
+    s = (rs.uniform(0.4, 1.0, n) + np.arange(n) * 1e-6).astype(np.float32)
+    lists = [[i] for i in range(n)]
+    poses = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+    poses[:, :3, 3] = rs.uniform(-2, 2, (n, 3)).astype(np.float32)
+    case = (t, R, s, lists, [0] * n, poses, np.arange(n, dtype=np.int64))
+    got, ref = _run_nms(api, case), _run_nms(port, case)
+    assert got[0] == ref[0] == [int(np.argmax(s))] and got[1] == ref[1]
+    assert got[2] == ref[2] and np.array_equal(got[4], ref[4])
+
+
 def test_nms_single_box_quirk():
     case = _nms_case(1, 0, 5)
     cfg = make_cfg("ca1m", pst_path=make_pst(32))
