@@ -344,7 +344,7 @@ struct __align__(16) bf_refine_smem {
     float vscore[BF_MAX_VIEWS];
     float col[3 * BF_MAX_VIEWS];
     int overflow;
-    // followed by: bf_view views[max_views]; float fit[P]; int sel[max_hits]; float contrib[pair_cap]
+    // followed by: bf_view views[max_views]; float fit[P]; int sel[max_hits]; float terms[8][max_hits]; float contrib[pair_cap]
 };
 
 extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
@@ -370,7 +370,8 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
     bf_view* views = (bf_view*)(sm + 1);
     float* fit = (float*)(views + max_views);
     int* sel = (int*)(fit + prm.P);
-    float* contrib = (float*)(sel + cfg.max_hits);
+    float* terms = (float*)(sel + cfg.max_hits);          // [8][max_hits] addends of cal_transform
+    float* contrib = terms + 8 * cfg.max_hits;
     if (tid == 0) sm->overflow = 0;
     if (V < 1 || V > max_views) {                        // flagged in status by bf_check_views_kernel2 (cluster-uniform)
         if (tid == 0 && crank == 0) { prm.out_updated[b] = 0; prm.out_iters[b] = 0; }
@@ -479,15 +480,21 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
                 __syncthreads();
             }
             const int hits = min(total, cfg.max_hits);
-            // sequential float32 accumulation in index order: 6 PST sums, weight sum, weighted-fitness sum
+            // the eight addends of every selected particle (6 x PST*w, w, fitness*w) are formed in parallel ...
+            for (int q = tid; q < hits; q += T) {
+                const int j = sel[q];
+                const float w = origin - fit[j];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) terms[k * cfg.max_hits + q] = __ldg(prm.pst + 6 * (size_t)j + k) * w;
+                terms[6 * cfg.max_hits + q] = w;
+                terms[7 * cfg.max_hits + q] = fit[j] * w;
+            }
+            __syncthreads();
+            // ... and accumulated sequentially in index order in float32, like the reference's Python loop (:490-515)
             if (tid < 8) {
                 float acc = 0.0f;
-                for (int q = 0; q < hits; ++q) {
-                    const int j = sel[q];
-                    const float w = origin - fit[j];
-                    const float term = (tid < 6) ? __ldg(prm.pst + 6 * (size_t)j + tid) * w : ((tid == 6) ? w : fit[j] * w);
-                    acc += term;
-                }
+                const float* tq = terms + tid * cfg.max_hits;
+                for (int q = 0; q < hits; ++q) acc += tq[q];
                 S->acc[tid] = acc;
             }
             __syncthreads();
@@ -554,7 +561,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
 
 static size_t bf_refine_smem_bytes(int P, int max_hits, int pair_cap, int max_views) {
     return sizeof(bf_refine_smem) + sizeof(bf_view) * (size_t)max_views + sizeof(float) * (size_t)P +
-           sizeof(int) * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + 16;
+           sizeof(int) * (size_t)max_hits + sizeof(float) * 8 * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + 16;
 }
 
 __global__ void bf_check_views_kernel(const int32_t* __restrict__ off, int B, int32_t* __restrict__ status) {
