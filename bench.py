@@ -224,8 +224,15 @@ def run_ours(args, rank, world, local_rank):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_ach = tot_ev * BYTES_PER_EVAL / (tot_ms * 1e-3) / 1e9
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of this command
+        traffic, tsrc = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_v6_refine_traffic.json")
+        if os.path.isfile(tpath):
+            tj = json.load(open(tpath))
+            traffic, tsrc = round(tj["dram_bytes_per_launch_mean"]), tj["source"]
         roof = {"bound": "fp32", "kernel": "bf_refine_kernel", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2),
-                "unit": "TFLOP/s", "frac": round(achieved / fp32_peak, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / fp32_peak, 4), "traffic": traffic, "traffic_unit": "bytes/launch",
+                "traffic_source": tsrc, "algorithmic_bytes_per_launch": round(tot_ev * BYTES_PER_EVAL / len(ref_ms)),
                 "peak_source": "bf_probe_fp32 FMA micro-benchmark on this device (burst); MEASURED_PEAKS.json has no FP32 entry",
                 "launches": len(ref_ms), "avg_launch_ms": round(tot_ms / len(ref_ms), 4),
                 "evals_per_launch": round(tot_ev / len(ref_ms), 1), "flop_per_eval": FLOP_PER_EVAL,
