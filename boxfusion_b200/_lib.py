@@ -31,6 +31,24 @@ class RefineCfg(ctypes.Structure):
                 ("max_hits", ctypes.c_int32), ("early_stop", ctypes.c_int32), ("views_total", ctypes.c_int32), ("max_views", ctypes.c_int32)]
 
 
+class MapBuffers(ctypes.Structure):
+    """bf_map_buffers"""
+    _fields_ = [(k, _vp) for k in ("tensor", "R", "scores", "box2d", "projxy", "pose", "uv", "valid", "init_id", "frame_id",
+                                   "fl", "flen")]
+
+
+class StoreBuffers(ctypes.Structure):
+    """bf_store_buffers"""
+    _fields_ = [(k, _vp) for k in ("tensor", "R", "scores", "uv", "pose")]
+
+
+class FusedTable(ctypes.Structure):
+    """bf_fused_table"""
+    _fields_ = [("lists", _vp), ("len", _vp), ("hash", _vp), ("count", _vp), ("cap", ctypes.c_int32)]
+
+
+_MBP, _SBP, _FTP = ctypes.POINTER(MapBuffers), ctypes.POINTER(StoreBuffers), ctypes.POINTER(FusedTable)
+
 # name -> (restype, argtypes); every symbol declared in include/boxfusion_b200.h
 PROTOTYPES = {
     "bf_version": (_i32, []),
@@ -48,6 +66,12 @@ PROTOTYPES = {
     "bf_pose_disparity": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bf_refine": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, ctypes.POINTER(RefineCfg),
                          _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bf_engine_ingest": (_i32, [_vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _MBP, _SBP, _vp, _vp]),
+    "bf_engine_corr": (_i32, [_vp, _MBP, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f64,
+                              _f32, _f32, _vp, _vp, _vp]),
+    "bf_engine_compact": (_i32, [_vp, _vp, _i32, _MBP, _MBP, _vp, _vp]),
+    "bf_engine_select": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp]),
+    "bf_engine_apply": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
 }

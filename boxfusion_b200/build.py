@@ -18,6 +18,7 @@ SOURCES = {
     "bf_geometry.cu": [],
     "bf_iou3d.cu": [],
     "bf_assoc.cu": [],
+    "bf_engine.cu": [],
     "bf_refine.cu": ["-fmad=false"],
 }
 

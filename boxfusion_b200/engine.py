@@ -1,0 +1,226 @@
+"""Device-resident fusion engine.
+
+`FusionEngine.step()` is one keyframe of demo.py:200-327 with *all* state resident in HBM: the global map
+(`all_pred_box`), the per-frame observation store (`per_frame_ins`) and BoxManager's `fusion_list`,
+`fusion_flag`, `already_fusion`.  Per keyframe the host issues one H2D copy (the packed detections), a fixed
+sequence of library calls, and reads back 32 bytes (row counts for the next launch configuration); results are
+downloaded only when asked for (`snapshot()`, `export()`).
+
+It computes exactly what the reference-shaped API (`Instances3D.spatial_association`, `correspondence_association`,
+`BoxManager.update`, `BoxFusion.boxfusion`) computes - tests/test_gpu_engine.py compares every field after every
+keyframe with the reference goldens - but is not itself part of the reference's interface; `export()` materialises
+the reference-shaped containers from the device state.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import FusedTable, MapBuffers, StoreBuffers, handle, ptr
+from .box_fusion import _load_pst
+
+_MAP_FIELDS = (("tensor", 6, torch.float32), ("R", 9, torch.float32), ("scores", 1, torch.float32),
+               ("box2d", 4, torch.float32), ("projxy", 2, torch.float32), ("pose", 16, torch.float32),
+               ("uv", 16, torch.float32), ("valid", 1, torch.float32), ("init_id", 1, torch.int32),
+               ("frame_id", 1, torch.int32), ("fl", ops.FUSION_CAP, torch.int32), ("flen", 1, torch.int32))
+_STORE_FIELDS = (("tensor", 6), ("R", 9), ("scores", 1), ("uv", 16), ("pose", 16))
+
+
+def pack_keyframe(tensor_cam, R_cam, scores, pred_boxes, pred_proj_xy, pose) -> np.ndarray:
+    """One contiguous float32 buffer per keyframe (the engine's only H2D): fields, then pose, then its inverses.
+    The inverses are taken on the host with the reference's own calls: torch.linalg.inv (instances.py:350) for the
+    observation projection and np.linalg.inv (instances.py:680) for the correspondence projection."""
+    pose = np.ascontiguousarray(pose, dtype=np.float32).reshape(4, 4)
+    inv_t = torch.linalg.inv(torch.from_numpy(pose)[None])[0].numpy()
+    inv_n = np.linalg.inv(pose).astype(np.float32)
+    parts = [np.asarray(a, dtype=np.float32).reshape(-1) for a in (tensor_cam, R_cam, scores, pred_boxes, pred_proj_xy)]
+    return np.ascontiguousarray(np.concatenate(parts + [pose.reshape(-1), inv_t.reshape(-1), inv_n.reshape(-1)]))
+
+
+class FusionEngine:
+    def __init__(self, cfg: dict, device="cuda", map_capacity: int = 4096, store_capacity: int = 65536,
+                 fused_capacity: int = 32768, iou_mode: int = ops.IOU_SAMPLED_REF):
+        if cfg["box_fusion"].get("check_valid"):
+            raise NotImplementedError("check_valid (box_manager.py:151-166) is not part of the device-resident engine")
+        self.cfg = cfg
+        self.dev = ops._dev(device if str(device) != "cuda" else None)
+        self.h = handle(self.dev)
+        self.iou_mode = iou_mode
+        self.ncap, self.mcap, self.fcap = int(map_capacity), int(store_capacity), int(fused_capacity)
+        d = self.dev
+        self._maps = [self._alloc_map() for _ in range(2)]          # ping-pong for compaction
+        self._cur = 0
+        self.store = {k: torch.zeros((self.mcap, w), dtype=torch.float32, device=d) for k, w in _STORE_FIELDS}
+        self._store_c = StoreBuffers(*[self.store[k].data_ptr() for k, _ in _STORE_FIELDS])
+        self.fflag = torch.zeros(self.mcap, dtype=torch.int32, device=d)
+        self.fused = {"lists": torch.zeros((self.fcap, ops.FUSION_CAP), dtype=torch.int32, device=d),
+                      "len": torch.zeros(self.fcap, dtype=torch.int32, device=d),
+                      "hash": torch.zeros(self.fcap, dtype=torch.int64, device=d),
+                      "count": torch.zeros(1, dtype=torch.int32, device=d)}
+        self._fused_c = FusedTable(self.fused["lists"].data_ptr(), self.fused["len"].data_ptr(), self.fused["hash"].data_ptr(),
+                                   self.fused["count"].data_ptr(), self.fcap)
+        self.keep = torch.zeros(self.ncap, dtype=torch.int32, device=d)
+        self.success = torch.zeros(self.ncap, dtype=torch.int32, device=d)
+        self.todo = torch.zeros(self.ncap, dtype=torch.int32, device=d)
+        self.offsets = torch.zeros(self.ncap + 1, dtype=torch.int32, device=d)
+        self.view_index = torch.zeros(self.ncap * ops.FUSION_CAP, dtype=torch.int32, device=d)
+        self.corners = torch.zeros((self.ncap, 8, 3), dtype=torch.float32, device=d)
+        self.centers = torch.zeros((self.ncap, 3), dtype=torch.float32, device=d)
+        self.out = torch.zeros((self.ncap, 6), dtype=torch.float32, device=d)
+        self.upd = torch.zeros(self.ncap, dtype=torch.int32, device=d)
+        self.its = torch.zeros(self.ncap, dtype=torch.int32, device=d)
+        self.info = torch.zeros(8, dtype=torch.int32, device=d)
+        self.status = torch.zeros(4, dtype=torch.int32, device=d)
+        self._info_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.pst = torch.from_numpy(_load_pst(cfg["box_fusion"]["pst_path"])).to(d)
+        cam = cfg["cam"]
+        self.K16 = np.array([[cam["fx"], 0, cam["cx"], 0], [0, cam["fy"], cam["cy"], 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float64)
+        self.H, self.W = cam["H"], cam["W"]
+        self.N = 0            # map rows
+        self.M = 0            # observations (= box_count = len(per_frame_ins) = len(fusion_flag))
+        self.count = 0        # keyframe counter
+        self.last = {"B": 0, "views": 0}
+        self.refine_log = None
+
+    def _alloc_map(self):
+        d = self.dev
+        t = {k: torch.zeros((self.ncap, w) if w > 1 else (self.ncap,), dtype=dt, device=d) for k, w, dt in _MAP_FIELDS}
+        t["_c"] = MapBuffers(*[t[k].data_ptr() for k, _, _ in _MAP_FIELDS])
+        return t
+
+    @property
+    def map(self):
+        return self._maps[self._cur]
+
+    def update_intrinsics(self, size, K):                     # box_fusion.py:463-466
+        self.H, self.W = size[1], size[0]
+        self.K16[:3, :3] = np.asarray(K)
+
+    # -----------------------------------------------------------------------------------------------------------
+    def step(self, packed, n: int, K, image_size) -> None:
+        """One keyframe.  `packed`: pack_keyframe() output as a (pinned) CPU tensor, numpy array or CUDA tensor."""
+        self.update_intrinsics(image_size, K)                 # demo.py:117-118 (update_K_flag stays False)
+        if n == 0:                                            # demo.py:206-212
+            self.count += 1
+            return
+        if self.N + n > self.ncap or self.M + n > self.mcap:
+            raise RuntimeError("FusionEngine capacity exceeded (map_capacity / store_capacity)")
+        h, lib, st = self.h, self.h.lib, self.h.stream()
+        if isinstance(packed, torch.Tensor):
+            if not packed.is_cuda:
+                ops.Profile.h2d_bytes += packed.numel() * 4
+            buf = packed.to(self.dev, non_blocking=True)
+        else:
+            buf = ops.dev_tensor(packed, torch.float32, self.dev)
+        K3 = np.asarray(K, dtype=np.float32)
+        fx, fy, cx, cy = float(K3[0, 0]), float(K3[1, 1]), float(K3[0, 2]), float(K3[1, 2])
+        Wf, Hf = float(image_size[0]), float(image_size[1])
+        mp = self.map
+        N0, M0 = self.N, self.M
+        ops._call(h, "bf_engine_ingest", lib.bf_engine_ingest, h.h, ptr(buf), n, fx, fy, cx, cy, Wf, Hf, self.count, M0, N0, M0, M0,
+                  ctypes.byref(mp["_c"]), ctypes.byref(self._store_c), ptr(self.fflag), st)
+        self.M = M0 + n
+        if N0 == 0:                                           # first keyframe: demo.py:228-243
+            self.N = n
+            self.count += 1
+            return
+        Nall = N0 + n
+        bm, bf = self.cfg["association"], self.cfg["box_fusion"]
+        # STEP 1: spatial association (demo.py:262)
+        ops._call(h, "bf_box_corners", lib.bf_box_corners, h.h, ptr(mp["tensor"]), ptr(mp["R"]), Nall, ptr(self.corners),
+                  ptr(self.centers), st)
+        order = torch.argsort(mp["scores"][:Nall], descending=True, stable=True).to(torch.int32)
+        ops._call(h, "bf_nms3d", lib.bf_nms3d, h.h, ptr(self.corners), ptr(self.centers), Nall, ptr(order), ptr(mp["init_id"]),
+                  ptr(self.store["pose"]), self.M, ptr(mp["fl"]), ptr(mp["flen"]), ptr(self.fflag), float(bf["nms_threshold"]),
+                  float(bm["translation_gap"]), float(bm["rotation_gap"]), 0.5, int(self.iou_mode), ptr(self.keep),
+                  ptr(self.success), ptr(self.status), st)
+        # STEP 2: correspondence association for small objects (demo.py:273-289) + valid_num of STEP 1
+        pinv_np = buf[22 * n + 32: 22 * n + 48]
+        ops._call(h, "bf_engine_corr", lib.bf_engine_corr, h.h, ctypes.byref(mp["_c"]), ptr(self.store["pose"]), ptr(self.fflag),
+                  N0, n, ptr(self.keep), ptr(self.success), ptr(pinv_np), fx, fy, cx, cy, Wf, Hf, float(np.float32(bf["small_size"])),
+                  float(np.float32(bf["small_size"] + 0.1)), float(bm["small_threshold"]), float(bm["translation_gap"]),
+                  float(bm["rotation_gap"]), ptr(self.info), ptr(self.status[1:]), st)
+        # all_pred_box[keep_idx]; box_manager.update(keep_idx) (demo.py:292 / 325-327)
+        other = self._maps[1 - self._cur]
+        ops._call(h, "bf_engine_compact", lib.bf_engine_compact, h.h, ptr(self.keep), Nall, ctypes.byref(mp["_c"]),
+                  ctypes.byref(other["_c"]), ptr(self.info), st)
+        self._cur = 1 - self._cur
+        mp = self.map
+        # STEP 3: multi-view box fusion (demo.py:304-305)
+        if bf["use"]:
+            ops._call(h, "bf_engine_select", lib.bf_engine_select, h.h, ctypes.byref(mp["_c"]), ctypes.byref(self._fused_c),
+                      ptr(self.info), ptr(self.todo), ptr(self.offsets), ptr(self.view_index), st)
+        self._info_host.copy_(self.info, non_blocking=True)   # the step's only D2H: 32 bytes
+        torch.cuda.current_stream(self.dev).synchronize()
+        ops.Profile.d2h_bytes += 32
+        info = self._info_host.numpy()
+        self.N = int(info[1])
+        B, SV, maxV = (int(info[2]), int(info[3]), int(info[4])) if bf["use"] else (0, 0, 0)
+        if info[5] != 0:
+            raise RuntimeError(f"FusionEngine: a fusion list has {maxV} views; bf_refine supports {ops.MAX_VIEWS}")
+        self.last = {"B": B, "views": SV}
+        if B > 0:
+            rcfg = ops.make_refine_cfg(self.cfg, self.K16.reshape(-1), self.H, self.W)
+            rcfg.views_total, rcfg.max_views = SV, maxV
+            ops._call(h, "bf_refine", lib.bf_refine, h.h, ptr(self.pst), self.pst.shape[0], ptr(self.store["tensor"]),
+                      ptr(self.store["R"]), ptr(self.store["scores"]), ptr(self.store["uv"]), ptr(self.store["pose"]), self.M,
+                      ptr(self.offsets), ptr(self.view_index), B, ctypes.byref(rcfg), ptr(self.out), ptr(self.upd), ptr(self.its),
+                      None, ptr(self.status[2:]), st)
+            ops._call(h, "bf_engine_apply", lib.bf_engine_apply, h.h, ctypes.byref(mp["_c"]), ctypes.byref(self._fused_c),
+                      ptr(self.fflag), ptr(self.info), ptr(self.todo), ptr(self.out), ptr(self.upd), ptr(self.status[3:]), st)
+            if self.refine_log is not None:
+                self.refine_log.append((B, SV))
+        self.count += 1
+
+    def check_status(self):
+        s = self.status.cpu().numpy()
+        if (s != 0).any():
+            raise RuntimeError(f"FusionEngine: capacity error reported by the device (status {s.tolist()})")
+
+    # -----------------------------------------------------------------------------------------------------------
+    def snapshot(self) -> dict:
+        """Everything the reference API would have mutated, downloaded (same keys as FusionSession.snapshot)."""
+        self.check_status()
+        N, mp = self.N, self.map
+        flen = mp["flen"][:N].cpu().numpy()
+        fl = mp["fl"][:N].cpu().numpy()
+        flat = np.concatenate([fl[i, :flen[i]] for i in range(N)]).astype(np.int64) if N else np.zeros(0, np.int64)
+        F = int(self.fused["count"].item())
+        al, aln = self.fused["lists"][:F].cpu().numpy(), self.fused["len"][:F].cpu().numpy()
+        aflat = np.concatenate([al[i, :aln[i]] for i in range(F)]).astype(np.int64) if F else np.zeros(0, np.int64)
+        return {"tensor": mp["tensor"][:N].cpu().numpy(), "R": mp["R"][:N].reshape(N, 3, 3).cpu().numpy(),
+                "scores": mp["scores"][:N].cpu().numpy(), "valid_num": mp["valid"][:N].cpu().numpy(),
+                "init_id": mp["init_id"][:N].cpu().numpy().astype(np.int64),
+                "fusion_flat": flat, "fusion_off": np.cumsum(np.concatenate([[0], flen])).astype(np.int64),
+                "fusion_flag": self.fflag[: self.M].cpu().numpy().astype(np.int64),
+                "already_flat": aflat, "already_off": np.cumsum(np.concatenate([[0], aln])).astype(np.int64)}
+
+    def export(self):
+        """(all_pred_box, per_frame_ins, box_manager) in the reference's container types, built from the device state."""
+        from . import api
+        self.check_status()
+        N, M, mp = self.N, self.M, self.map
+        a = api.Instances3D((int(self.H), int(self.W)))
+        a.scores, a.pred_boxes, a.pred_proj_xy = mp["scores"][:N].clone(), mp["box2d"][:N].clone(), mp["projxy"][:N].clone()
+        a.pred_boxes_3d = api.GeneralInstance3DBoxes(mp["tensor"][:N], mp["R"][:N].reshape(N, 3, 3))
+        a.cam_pose = mp["pose"][:N].reshape(N, 4, 4).clone()
+        a.frame_id, a.init_id = mp["frame_id"][:N].to(torch.int64), mp["init_id"][:N].to(torch.int64)
+        a.valid_num, a.projected_boxes = mp["valid"][:N].clone(), mp["uv"][:N].reshape(N, 8, 2).clone()
+        p = api.Instances3D((int(self.H), int(self.W)))
+        p.scores = self.store["scores"][:M, 0].clone()
+        p.pred_boxes_3d = api.GeneralInstance3DBoxes(self.store["tensor"][:M], self.store["R"][:M].reshape(M, 3, 3))
+        p.cam_pose = self.store["pose"][:M].reshape(M, 4, 4).clone()
+        p.projected_boxes = self.store["uv"][:M].reshape(M, 8, 2).clone()
+        bm = api.BoxManager(self.cfg)
+        snap = self.snapshot()
+        off, flat = snap["fusion_off"], snap["fusion_flat"]
+        bm.fusion_list = [[int(x) for x in flat[off[i]:off[i + 1]]] for i in range(N)]
+        bm.fusion_flag = [int(x) for x in snap["fusion_flag"]]
+        bm.last_fusion_frame = [[0] for _ in range(M)]
+        aoff, aflat = snap["already_off"], snap["already_flat"]
+        bm.already_fusion = [[int(x) for x in aflat[aoff[i]:aoff[i + 1]]] for i in range(len(aoff) - 1)]
+        return a, p, bm

@@ -20,7 +20,9 @@ MAX_VIEWS = 64
 
 # kernels launched by one call of each entry point (the library's own __global__ functions)
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
-                    "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1}
+                    "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1,
+                    "bf_engine_ingest": 1, "bf_engine_corr": 1, "bf_engine_compact": 2, "bf_engine_select": 1,
+                    "bf_engine_apply": 1}
 
 
 class Profile:

@@ -140,6 +140,44 @@ int bf_evaluate_iou(bf_handle* h, const float* pst /*[P,6]*/, int P, const float
                     const float* uv /*[V,16]*/, const float* poses /*[V,16]*/, int V, const float* search6,
                     const bf_refine_cfg* cfg /*host*/, float* fitness /*[P]*/, void* stream);
 
+/* ---- Device-resident map store ------------------------------------------------
+ * The state demo.py keeps in Python containers across keyframes (all_pred_box, per_frame_ins, BoxManager's
+ * fusion_list / fusion_flag / already_fusion; demo.py:72-83, 243-327) held in caller-owned device buffers, with the
+ * host bookkeeping around bf_nms3d / bf_refine done by kernels.  boxfusion_b200/engine.py drives them. */
+typedef struct {            /* one row per map box (`all_pred_box`), capacity rows each */
+    float* tensor; float* R; float* scores; float* box2d; float* projxy; float* pose; float* uv; float* valid;
+    int32_t* init_id; int32_t* frame_id; int32_t* fl /*[cap,BF_FUSION_CAP]*/; int32_t* flen;
+} bf_map_buffers;
+typedef struct {            /* one row per observation ever made (`per_frame_ins`) */
+    float* tensor; float* R; float* scores; float* uv; float* pose;
+} bf_store_buffers;
+typedef struct {            /* BoxManager.already_fusion */
+    int32_t* lists /*[cap,BF_FUSION_CAP]*/; int32_t* len; unsigned long long* hash; int32_t* count /*[1]*/; int32_t cap;
+} bf_fused_table;
+
+/* demo.py:216-221, 243/248, 253-254: lift + project the keyframe's n detections and append them to map rows [N,N+n)
+ * and store rows [M,M+n).  packed = tensor_cam[n,6] R_cam[n,9] scores[n] box2d[n,4] projxy[n,2] pose[16] pose_inv[16]. */
+int bf_engine_ingest(bf_handle* h, const float* packed, int n, float fx, float fy, float cx, float cy, float W, float H,
+                     int frame_id, int box_count, int N, int M, int D, const bf_map_buffers* mp /*host*/,
+                     const bf_store_buffers* st /*host*/, int32_t* fflag, void* stream);
+/* instances.py:411-490 + box_manager.py:90-129 on the keep/success flags bf_nms3d produced; also applies valid_num += 1
+ * of nms_3d (instances.py:72-73).  info[0] <- 1 if any new box survived nms_3d (demo.py:269). */
+int bf_engine_corr(bf_handle* h, const bf_map_buffers* mp /*host*/, const float* store_poses, int32_t* fflag, int N_glo, int n,
+                   int32_t* keep, const int32_t* success, const float* pose_inv_np /*[16]*/, float fx, float fy, float cx,
+                   float cy, float W, float H, float small_size, float small_plus, double threshold, float translation_gap,
+                   float rotation_gap, int32_t* info, int32_t* status, void* stream);
+/* `all_pred_box[keep_idx]` + `box_manager.update(keep_idx)` (demo.py:292, 325-327): stable compaction of every map
+ * field from `from` into `to`; info[1] <- new row count. */
+int bf_engine_compact(bf_handle* h, const int32_t* keep, int N, const bf_map_buffers* from /*host*/,
+                      const bf_map_buffers* to /*host*/, int32_t* info, void* stream);
+/* box_fusion.py:631-635: rows with >= 3 views whose view set was not fused before -> todo[], CSR for bf_refine;
+ * info[2] = B, info[3] = sum of views, info[4] = max views, info[5] = status. */
+int bf_engine_select(bf_handle* h, const bf_map_buffers* mp /*host*/, const bf_fused_table* ft /*host*/, int32_t* info,
+                     int32_t* todo, int32_t* offsets, int32_t* view_index, void* stream);
+/* box_fusion.py:716-724: write bf_refine's rows into the map, set fusion flags, extend already_fusion. */
+int bf_engine_apply(bf_handle* h, const bf_map_buffers* mp /*host*/, const bf_fused_table* ft /*host*/, int32_t* fflag,
+                    const int32_t* info, const int32_t* todo, const float* out, const int32_t* upd, int32_t* status, void* stream);
+
 /* Diagnostic: measured FP32 FMA throughput (TFLOP/s) of the device - the denominator of the FP32-pipe
  * roofline bench.py reports.  Synchronous; outputs are HOST pointers. */
 int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host or NULL*/);

@@ -1,0 +1,86 @@
+"""GPU tests of the device-resident engine: after every keyframe its state must equal what
+the reference-shaped API - and the reference itself (goldens) - produce."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from boxfusion_b200 import api                                        # noqa: E402
+from boxfusion_b200.driver import FusionSession                       # noqa: E402
+from boxfusion_b200.engine import FusionEngine, pack_keyframe         # noqa: E402
+from boxfusion_b200.synthetic import SyntheticScene, make_cfg, make_pst   # noqa: E402
+from tests.golden.make_golden import SEQUENCES                        # noqa: E402
+
+KEYS = ("tensor", "R", "scores", "valid_num", "init_id", "fusion_flat", "fusion_off", "fusion_flag", "already_flat", "already_off")
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8) if a.dtype.kind == "f" else a
+
+
+def _pack(kf):
+    return pack_keyframe(kf.tensor_cam, kf.R_cam, kf.scores, kf.pred_boxes, kf.pred_proj_xy, kf.pose)
+
+
+@pytest.mark.parametrize("name", list(SEQUENCES))
+def test_engine_matches_reference_golden(golden_dir, name):
+    spec = dict(SEQUENCES[name])
+    n_frames = spec.pop("frames")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    scene = SyntheticScene(**spec)
+    cfg = make_cfg(spec["shape"], pst_path=os.path.join(golden_dir, "pst_1024_0.npy"), pst_size=1024)
+    eng = FusionEngine(cfg, map_capacity=512, store_capacity=4096, fused_capacity=1024)
+    M = 0
+    for k in range(n_frames):
+        kf = scene.keyframe(k)
+        n = kf.tensor_cam.shape[0]
+        eng.step(_pack(kf), n, kf.K, kf.image_size)
+        # the engine lifts and projects by itself: the stored observations must be the reference's tensors
+        assert np.array_equal(_bits(eng.store["tensor"][M:M + n].cpu().numpy()), _bits(g[f"k{k}_tensor_w"]))
+        np.testing.assert_allclose(eng.store["uv"][M:M + n].cpu().numpy().reshape(n, 8, 2), g[f"k{k}_projected"], rtol=1e-6, atol=1e-4)
+        M += n
+        snap = eng.snapshot()
+        for key in KEYS:
+            ref = g[f"k{k}_snap_{key}"]
+            assert snap[key].shape == ref.shape and np.array_equal(_bits(snap[key]), _bits(ref)), (name, k, key)
+
+
+def test_engine_matches_api_longer_sequence():
+    """60 dense keyframes: the engine against the reference-shaped CUDA API (itself pinned to the reference)."""
+    scene = SyntheticScene(n_objects=150, seed=9, max_det=45, shape="ca1m", tilt_noise=0.01)
+    cfg = make_cfg("ca1m", pst_path=make_pst(512, seed=0), pst_size=512)
+    eng = FusionEngine(cfg, map_capacity=2048, store_capacity=8192)
+    sess = FusionSession(api, cfg, device="cuda")
+    for k in range(60):
+        kf = scene.keyframe(k)
+        eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+        sess.step(kf)
+        a, b = eng.snapshot(), sess.snapshot()
+        for key in KEYS:
+            assert a[key].shape == b[key].shape and np.array_equal(_bits(a[key]), _bits(b[key])), (k, key)
+    assert len(sess.box_manager.already_fusion) > 50 and eng.N == len(sess.all_pred_box)
+    # export(): the reference-shaped containers rebuilt from the device state
+    allp, per, bm = eng.export()
+    assert bm.fusion_list == [[int(x) for x in l] for l in sess.box_manager.fusion_list]
+    assert bm.already_fusion == [[int(x) for x in l] for l in sess.box_manager.already_fusion]
+    assert torch.equal(allp.pred_boxes_3d.tensor.cpu(), sess.all_pred_box.pred_boxes_3d.tensor.cpu())
+    assert torch.equal(per.projected_boxes.cpu(), sess.per_frame_ins.projected_boxes.cpu())
+
+
+def test_engine_empty_keyframe_and_capacity():
+    scene = SyntheticScene(n_objects=20, seed=2, max_det=8)
+    cfg = make_cfg("ca1m", pst_path=make_pst(64), pst_size=64)
+    eng = FusionEngine(cfg, map_capacity=16, store_capacity=64, fused_capacity=16)
+    kf = scene.keyframe(0)
+    eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+    n0 = eng.N
+    eng.step(np.zeros(48, np.float32), 0, kf.K, kf.image_size)           # empty keyframe: demo.py:206-212
+    assert eng.N == n0 and eng.count == 2
+    with pytest.raises(RuntimeError):
+        for k in range(1, 20):
+            kf = scene.keyframe(k)
+            eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
