@@ -72,6 +72,7 @@ PROTOTYPES = {
     "bf_engine_compact": (_i32, [_vp, _vp, _i32, _MBP, _MBP, _vp, _vp]),
     "bf_engine_select": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp]),
     "bf_engine_apply": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bf_detection_filter": (_i32, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _f64, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
 }

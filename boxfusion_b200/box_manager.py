@@ -176,6 +176,15 @@ class BoxManager:
                     self.fusion_flag[cur_id] = 1
         return keep
 
+    def filter_detections(self, pred_instances, W, H, score_thresh=0.0):
+        """demo.py:138-148 fused (score threshold + the three masks below) -> bool keep mask, one kernel.  The individual
+        check_* methods below keep the reference's signatures."""
+        det = self.cfg["detection"]
+        keep, _ = ops.detection_filter(pred_instances.pred_boxes_3d.tensor, pred_instances.pred_proj_xy, pred_instances.scores,
+                                       W, H, float(score_thresh), det["uv_bound_value"] if det.get("uv_bound") else None,
+                                       det["floor_ratio"] if det.get("floor_mask") else None, det.get("size_max_thres") or None)
+        return keep
+
     # ---- detection pre-filters (box_manager.py:217-245): stay in torch on the detector's device -----
     def check_uv_bounds(self, uv_coords, W, H, ratio=1.0):
         gap_W, gap_H = int((1 - ratio) * W), int((1 - ratio) * H)

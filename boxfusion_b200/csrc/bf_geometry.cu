@@ -134,3 +134,48 @@ extern "C" int bf_pose_disparity(bf_handle* h, const float* poses, const int32_t
     BF_LAUNCH_CHECK(h, "bf_pose_disparity_kernel");
     return BF_OK;
 }
+
+// Detection pre-filters of demo.py:138-148 in one pass: score threshold, check_uv_bounds
+// (box_manager.py:217-225), check_floor_mask (:227-237), check_large_mask (:239-245).  flags bit0 = score below
+// threshold, bit1 = centre outside the shrunken image, bit2 = floor-like, bit3 = too large; keep[i] = (flags == 0).
+__global__ void bf_detection_filter_kernel(const float* __restrict__ xyzlhw, const float* __restrict__ proj_xy,
+                                           const float* __restrict__ scores, int n, float score_thresh, int use_uv,
+                                           float gap_w, float gap_h, float W, float H, int use_floor, float ratio,
+                                           int use_large, float size_max, int32_t* __restrict__ flags, int32_t* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int f = 0;
+    if (!(scores[i] >= score_thresh)) f |= 1;
+    if (use_uv) {
+        const float u = proj_xy[2 * i], v = proj_xy[2 * i + 1];
+        if (!((u > gap_w) && (u < (W - gap_w)) && (v > gap_h) && (v < (H - gap_h)))) f |= 2;
+    }
+    const float a = xyzlhw[6 * i + 3], b = xyzlhw[6 * i + 4], c = xyzlhw[6 * i + 5];
+    const float mx = fmaxf(a, fmaxf(b, c)), mn = fminf(a, fminf(b, c));
+    const float second = fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));            // median of three
+    if (use_floor) {
+        const float half = ratio * 0.5f;
+        const bool m1 = __fdiv_rn(mx, mn) > ratio;
+        const bool m2 = (__fdiv_rn(mx, mn) > half) && (__fdiv_rn(mx, second) > half) && (__fdiv_rn(second, mn) < 2.0f) &&
+                        (second < 0.15f) && (mn < 0.15f);
+        if (m1 || m2) f |= 4;
+    }
+    if (use_large && mx > size_max) f |= 8;
+    flags[i] = f;
+    keep[i] = (f == 0) ? 1 : 0;
+}
+
+extern "C" int bf_detection_filter(bf_handle* h, const float* xyzlhw, const float* proj_xy, const float* scores, int n,
+                                   float score_thresh, int use_uv, double uv_ratio, float W, float H, int use_floor, float floor_ratio,
+                                   int use_large, float size_max, int32_t* flags, int32_t* keep, void* stream) {
+    if (!h || n < 0 || (n > 0 && (!xyzlhw || !proj_xy || !scores || !flags || !keep)))
+        return bf_fail(h, BF_ERR_INVALID_ARG, "bf_detection_filter", "bad argument");
+    if (n == 0) return BF_OK;
+    // gap = int((1 - ratio) * size), evaluated in double like the Python expression (box_manager.py:218-219)
+    const float gap_w = (float)(int)((1.0 - uv_ratio) * (double)W), gap_h = (float)(int)((1.0 - uv_ratio) * (double)H);
+    bf_detection_filter_kernel<<<bf_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, proj_xy, scores, n, score_thresh, use_uv,
+                                                                                gap_w, gap_h, W, H, use_floor, floor_ratio, use_large,
+                                                                                size_max, flags, keep);
+    BF_LAUNCH_CHECK(h, "bf_detection_filter_kernel");
+    return BF_OK;
+}

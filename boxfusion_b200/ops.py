@@ -22,7 +22,7 @@ MAX_VIEWS = 64
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
                     "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1,
                     "bf_engine_ingest": 1, "bf_engine_corr": 1, "bf_engine_compact": 2, "bf_engine_select": 1,
-                    "bf_engine_apply": 1}
+                    "bf_engine_apply": 1, "bf_detection_filter": 1}
 
 
 class Profile:
@@ -257,3 +257,20 @@ def probe_fp32(iters: int = 4096, device=None) -> float:
     ms = ctypes.c_float(0.0)
     h.check(h.lib.bf_probe_fp32(h.h, int(iters), ctypes.byref(tf), ctypes.byref(ms)), "bf_probe_fp32")
     return float(tf.value)
+
+
+def detection_filter(xyzlhw, proj_xy, scores, W: float, H: float, score_thresh: float, uv_ratio: Optional[float] = None,
+                     floor_ratio: Optional[float] = None, size_max: Optional[float] = None):
+    """demo.py:138-148 in one kernel: (keep[n] bool, flags[n] int32: bit0 score, bit1 uv bounds, bit2 floor, bit3 large)."""
+    dev = _pick_device(xyzlhw, proj_xy, scores)
+    t = dev_tensor(xyzlhw, torch.float32, dev).reshape(-1, 6)
+    p = dev_tensor(proj_xy, torch.float32, dev).reshape(-1, 2)
+    s = dev_tensor(scores, torch.float32, dev).reshape(-1)
+    n = t.shape[0]
+    flags = torch.empty(n, dtype=torch.int32, device=dev)
+    keep = torch.empty(n, dtype=torch.int32, device=dev)
+    h = handle(dev)
+    _call(h, "bf_detection_filter", h.lib.bf_detection_filter, h.h, ptr(t), ptr(p), ptr(s), n, float(score_thresh),
+          int(uv_ratio is not None), float(uv_ratio or 0.0), float(W), float(H), int(floor_ratio is not None),
+          float(floor_ratio or 0.0), int(bool(size_max)), float(size_max or 0.0), ptr(flags), ptr(keep), h.stream())
+    return keep.bool(), flags

@@ -178,6 +178,14 @@ int bf_engine_select(bf_handle* h, const bf_map_buffers* mp /*host*/, const bf_f
 int bf_engine_apply(bf_handle* h, const bf_map_buffers* mp /*host*/, const bf_fused_table* ft /*host*/, int32_t* fflag,
                     const int32_t* info, const int32_t* todo, const float* out, const int32_t* upd, int32_t* status, void* stream);
 
+/* ---- Detection pre-filters in one pass (demo.py:138-148) -------------------------
+ * score >= score_thresh, BoxManager.check_uv_bounds (box_manager.py:217-225, uv_ratio is the Python double),
+ * check_floor_mask (:227-237), check_large_mask (:239-245).  flags: bit0 score, bit1 uv, bit2 floor, bit3 large;
+ * keep[i] = (flags[i] == 0). */
+int bf_detection_filter(bf_handle* h, const float* xyzlhw /*[n,6]*/, const float* proj_xy /*[n,2]*/, const float* scores /*[n]*/,
+                        int n, float score_thresh, int use_uv, double uv_ratio, float W, float H, int use_floor, float floor_ratio,
+                        int use_large, float size_max, int32_t* flags /*[n]*/, int32_t* keep /*[n]*/, void* stream);
+
 /* Diagnostic: measured FP32 FMA throughput (TFLOP/s) of the device - the denominator of the FP32-pipe
  * roofline bench.py reports.  Synchronous; outputs are HOST pointers. */
 int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host or NULL*/);

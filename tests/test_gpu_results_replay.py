@@ -69,3 +69,31 @@ def test_record_and_replay(tmp_path):
     a, b = eng.snapshot(), sess.snapshot()
     for key in ("tensor", "scores", "fusion_flat", "fusion_off", "already_flat"):
         assert np.array_equal(a[key], b[key]), key
+
+
+def test_detection_filter_matches_reference_masks():
+    """the fused pre-filter equals demo.py:138-148 applied with the reference's torch code (the port)."""
+    rs = np.random.RandomState(0)
+    n = 4000
+    dims = np.exp(rs.normal(np.log(0.4), 1.0, (n, 3))).astype(np.float32)
+    dims[:200, 0] = 3.0; dims[:200, 1] = 0.05                                  # floor-like slabs
+    dims[200:300] = np.array([0.14, 0.13, 1.2], np.float32) * rs.uniform(0.9, 1.1, (100, 3)).astype(np.float32)
+    t = np.concatenate([rs.normal(0, 2, (n, 3)).astype(np.float32), dims], 1)
+    uv = np.stack([rs.uniform(-20, 404, n), rs.uniform(-20, 532, n)], 1).astype(np.float32)
+    sc = rs.uniform(0, 1, n).astype(np.float32)
+    for shape, size_max in (("ca1m", 0), ("scannet", 2.5)):
+        cfg = make_cfg(shape)
+        cfg["detection"]["size_max_thres"] = size_max
+        W, H = cfg["cam"]["W"], cfg["cam"]["H"]
+        thr = cfg["detection"]["score_thresh"]
+        ref_bm = port.BoxManager(cfg)
+        tt, uu, ss = torch.from_numpy(t), torch.from_numpy(uv), torch.from_numpy(sc)
+        expect = (ss >= float(thr)) & ref_bm.check_uv_bounds(uu, W, H, ratio=cfg["detection"]["uv_bound_value"]) & \
+                 ~ref_bm.check_floor_mask(tt, ratio=cfg["detection"]["floor_ratio"])
+        if size_max:
+            expect = expect & ~ref_bm.check_large_mask(tt, thres=size_max)
+        ins = api.Instances3D((H, W))
+        ins.pred_boxes_3d = api.GeneralInstance3DBoxes(tt.cuda(), torch.eye(3).repeat(n, 1, 1).cuda())
+        ins.pred_proj_xy, ins.scores = uu.cuda(), ss.cuda()
+        got = api.BoxManager(cfg).filter_detections(ins, W, H, score_thresh=thr)
+        assert torch.equal(got.cpu(), expect) and 0.05 < float(expect.float().mean()) < 0.95
