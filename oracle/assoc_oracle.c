@@ -14,8 +14,8 @@
  * instances.py:532-533,563.  For 8 box corners in float32 the hull is unique: every box face is
  * split into two triangles along the convex diagonal and Qhull reports one unit-normal plane per
  * triangle (12 rows).  `bfo_hull_planes` recomputes exactly those 12 planes in double from the
- * float32 corners; tests/test_oracle_pinning.py checks them against scipy's `equations` (agreement
- * <= 1e-14) and oracle/assoc_oracle.py keeps a slow scipy-based twin for pinning against the
+ * float32 corners; tests/test_oracle_golden.py checks them against scipy's `equations` (agreement
+ * <= 1e-14) and oracle/port.py keeps a slow scipy-based twin (obb_counts_scipy) for pinning against the
  * reference itself.  np.linspace on float32 end points is float32 under NumPy 2:
  * x_i = fl(fl(i*step)+start), step = fl(fl(stop-start)/24), x_24 = stop.
  */
@@ -145,5 +145,14 @@ void bfo_corners(const float* tensor /*[N,6]*/, const float* R /*[N,9]*/, int N,
             for (int j = 0; j < 3; ++j)
                 out[24 * n + 3 * i + j] = ((r[3 * j] * vx + r[3 * j + 1] * vy) + r[3 * j + 2] * vz) + t[j];
         }
+    }
+}
+
+/* calculate_obb_iou (instances.py:106-125): one box against k others, IoU in float64; OpenMP over the others */
+void bfo_obb_iou_one_vs_many(const float* c1, const float* others /*[k,8,3]*/, int k, double* iou /*[k]*/) {
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < k; ++i) {
+        int32_t cnt[3];
+        iou[i] = bfo_obb_counts(c1, others + 24 * i, cnt) ? bfo_iou_from_counts(cnt) : 0.0;
     }
 }

@@ -17,12 +17,13 @@ Restates (paths relative to /root/reference; every function cites its lines):
 Pinning: no reference tests/golden vectors exist for this path; the port is pinned
 by running the unmodified reference in the build container on the same synthetic sequences and
 comparing every mutated field bit for bit (tests/golden/make_golden.py -> tests/golden/*.npz,
-tests/test_oracle_pinning.py).  Environment of record: numpy 2.3.5, scipy 1.18.1 (Qhull), torch 2.11
+tests/test_oracle_golden.py).  Environment of record: numpy 2.3.5, scipy 1.18.1 (Qhull), torch 2.11
 (SURVEY F8).
 
 `IOU_BACKEND`:
   "scipy" - half-spaces from scipy.spatial.ConvexHull exactly as the reference (slow; the CPU baseline)
   "c"     - half-spaces recomputed by oracle/assoc_oracle.c (fast; identical counts, see its header)
+  "c_batch" - as "c", one OpenMP-parallel C call per NMS head (bench.py's multi-core C baseline)
 """
 from __future__ import annotations
 
@@ -55,6 +56,7 @@ def _lib():
         _LIB.bfo_obb_counts.restype = ctypes.c_int
         _LIB.bfo_obb_counts_pairs.argtypes = [_FP, _IP, _IP, ctypes.c_int, _IP, _IP]
         _LIB.bfo_corners.argtypes = [_FP, _FP, ctypes.c_int, _FP]
+        _LIB.bfo_obb_iou_one_vs_many.argtypes = [_FP, _FP, ctypes.c_int, _DP]
     return _LIB
 
 
@@ -127,6 +129,13 @@ def obb_iou(c1, c2):
 
 
 def calculate_obb_iou(corners1, corners_others):         # instances.py:106-125
+    if IOU_BACKEND == "c_batch":                          # same values as "c", one call (OpenMP inside) per head
+        a = np.ascontiguousarray(corners1, dtype=np.float32)
+        b = np.ascontiguousarray(corners_others, dtype=np.float32)
+        out = np.zeros(b.shape[0], dtype=np.float64)
+        if b.shape[0]:
+            _lib().bfo_obb_iou_one_vs_many(a.ctypes.data_as(_FP), b.ctypes.data_as(_FP), b.shape[0], out.ctypes.data_as(_DP))
+        return out
     return np.asarray([obb_iou(corners1, corners_others[i]) for i in range(corners_others.shape[0])])
 
 

@@ -14,7 +14,7 @@
  * Pinning: the reference has no tests or golden vectors for this path.  This file
  * is pinned against the reference itself executed in the build container: (i) the kernel string
  * compiled verbatim for the host (oracle/_ref/libref_kernel.so, recipe oracle/ref_harness.py) and
- * (ii) the reference's own Python optimiser loop run over that kernel; tests/test_oracle_pinning.py
+ * (ii) the reference's own Python optimiser loop run over that kernel; tests/test_oracle_golden.py
  * and tests/golden/make_golden.py hold the comparisons (bit-exact on every compared float).
  *
  * Numeric model: float32 exactly where the reference uses float, double where it uses double
@@ -171,7 +171,7 @@ float bfo_eval_particle_view(const float* box6, const float* t_c16, const float*
     const int nt = hull2d(tgt, 8, ht);
     const int nc = poly_intersection(h0, n0, ht, nt, cand);
     const int ni = hull2d(cand, nc, hi);
-    if (nc > g_max_cand) g_max_cand = nc;
+    if (nc > g_max_cand) g_max_cand = nc;              /* diagnostics only; benign race under OpenMP */
     if (ni > g_max_inter_hull) g_max_inter_hull = ni;
     const float ai = shoelace(hi, ni), a0 = shoelace(h0, n0), at = shoelace(ht, nt);
     const float uni = a0 + at - ai;
@@ -187,6 +187,9 @@ void bfo_evaluate(const float* box6, const float* t_c /*[V,16]*/, const float* p
                   const float* rot9, const float* poses /*[V,16]*/, int V, const float* K16,
                   const float* search6, float img_h, float img_w, float* fitness /*[P]*/) {
     const float fx = K16[0], cx = K16[2], fy = K16[5], cy = K16[6];
+    /* particles are independent: OpenMP only changes who computes which fitness value (bench.py's multi-core C baseline;
+     * OMP_NUM_THREADS=1 is the single-threaded restatement used for pinning) */
+#pragma omp parallel for schedule(static) if (P >= 256)
     for (int p = 0; p < P; ++p) {
         float value = 0.0f, count = 0.0f;
         if (p < n_eval)

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY - ctypes view of oracle/refine_oracle.c plus the list-driven outer loop
 of `BoxFusion.boxfusion` (reference boxfusion/box_fusion.py:622-724).
 
-Pinned against the reference executed in the build container (tests/test_oracle_pinning.py,
+Pinned against the reference executed in the build container (tests/test_oracle_golden.py,
 tests/golden/make_golden.py).  Never imported by the product path.
 """
 from __future__ import annotations

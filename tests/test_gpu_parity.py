@@ -167,6 +167,25 @@ def test_nms_matches_port(n_map, n_det, seed, monkeypatch):
     assert len(ref[1]) > 10 and any(len(l) > 2 for l in ref[2])
 
 
+def test_nms_analytic_mode_matches_oracle(monkeypatch):
+    """Association with IOU_MODE = ANALYTIC: same greedy/record logic, IoU from the float64 analytic definition
+    (oracle/analytic_oracle.py) - keep/success/lists must equal the port run with that IoU."""
+    from boxfusion_b200 import instances as inst_mod
+    case = _nms_case(150, 60, 8, tilt=0.0)                               # gravity-aligned: every overlapping pair is co-axial
+
+    def analytic_iou(c1, c2):
+        lo1, hi1, lo2, hi2 = c1.min(0), c1.max(0), c2.min(0), c2.max(0)
+        if np.any(lo1 > hi2 + np.float32(1e-4)) or np.any(lo2 > hi1 + np.float32(1e-4)):
+            return 0.0
+        return analytic_oracle.iou_pair(np.asarray(c1, np.float32), np.asarray(c2, np.float32))
+
+    monkeypatch.setattr(port, "obb_iou", analytic_iou)
+    monkeypatch.setattr(inst_mod, "IOU_MODE", ops.IOU_ANALYTIC)
+    got, ref = _run_nms(api, case), _run_nms(port, case)
+    assert got[0] == ref[0] and got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3]
+    assert len(ref[1]) > 10
+
+
 def test_nms_dense_fallback_when_edge_list_overflows(monkeypatch):
     """> 8192 over-threshold pairs (a pile of near-identical boxes) take the dense bit-mask kernel."""
     monkeypatch.setattr(port, "IOU_BACKEND", "c")
