@@ -353,8 +353,9 @@ def run_c5(args, rank, world, local_rank):
 
 def cpu_port_run(frames, budget_s, backend="scipy"):
     """Reference algorithm on the host (oracle/port.py): frames processed within `budget_s`."""
-    from oracle import port
+    from oracle import port, refine_oracle
     port.IOU_BACKEND = backend
+    refine_oracle.set_threads(os.cpu_count() if backend == "c_batch" else 1)
     cfg = make_cfg("ca1m", pst_path=GOLDEN_PST, pst_size=1024)
     sess = FusionSession(port, cfg)
     t0 = time.perf_counter()

@@ -25,6 +25,18 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* threads used by the OpenMP loops of this library (1 = the single-threaded restatement; bench.py's faithful CPU arm) */
+void bfo_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : 1);
+#else
+    (void)n;
+#endif
+}
 
 typedef struct { float x, y; } pt2;
 

@@ -53,7 +53,15 @@ def lib():
         _LIB.bfo_reset_stats.restype = None
         _LIB.bfo_get_stats.restype = None
         _LIB.bfo_get_stats.argtypes = [_IP, _IP]
+        _LIB.bfo_set_threads.restype = None
+        _LIB.bfo_set_threads.argtypes = [ctypes.c_int]
+        _LIB.bfo_set_threads(1)           # single-threaded unless a caller asks otherwise (set_threads)
     return _LIB
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads of the C oracle (IoU pairs, particles); 1 = faithful single-threaded restatement."""
+    lib().bfo_set_threads(int(n))
 
 
 def _f(a):
