@@ -158,8 +158,8 @@ def run_ours(args, rank, world, local_rank):
         kf._resident = kf._pinned.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def run_pass(frames_by_seq, resident, timing, log):
-        ops.Profile.reset(timing=timing)
+    def run_pass(frames_by_seq, resident, timing, log, names=None):
+        ops.Profile.reset(timing=timing, names=names)
         evs, calls = [], []
         for frames in frames_by_seq:
             sess = FusionSession(api, cfg, device=str(dev))
@@ -190,11 +190,14 @@ def run_ours(args, rank, world, local_rank):
     # ---- pass 1: inputs resident in HBM -> `value`, roofline ------------------------------------------------
     sampler = ClockSampler(local_rank)
     barrier(); sampler.start(); t0 = time.perf_counter()
-    step_ms, calls, sess = run_pass(seqs, True, True, True)
+    step_ms, calls, sess = run_pass(seqs, True, True, True, names={"bf_refine"})     # events only around the dominant kernel
     barrier(); wall_resident = time.perf_counter() - t0
     launches = ops.Profile.launches
     per_call = ops.Profile.elapsed_ms()
     call_counts = dict(ops.Profile.calls)
+    # device time of every entry point: a separate, untimed-for-throughput pass with events around each C call
+    run_pass(seqs, True, True, False)
+    per_call_all = ops.Profile.elapsed_ms()
     # ---- pass 2: host inputs, H2D + D2H inside the timed region -> `e2e` -----------------------------------
     barrier(); t0 = time.perf_counter()
     step_ms_e2e, _, sess2 = run_pass(seqs, False, False, False)
@@ -269,7 +272,7 @@ def run_ours(args, rank, world, local_rank):
                 "share_of_step": round(tot_ms / sum(step_ms), 4),
                 "hbm": {"achieved": round(hbm_ach, 3), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 6),
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
-    kernel_ms = {k: round(sum(ms for ms, _ in v), 3) for k, v in per_call.items()}
+    kernel_ms = {k: round(sum(ms for ms, _ in v), 3) for k, v in per_call_all.items()}
     out = {
         "metric": "fusion keyframes/s (= 1000 / fusion ms/frame), association + particle refine per keyframe",
         "value": round(total_frames / t_res, 3), "unit": "keyframes/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),

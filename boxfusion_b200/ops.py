@@ -32,11 +32,12 @@ class Profile:
     h2d_bytes = 0        # host->device bytes moved by the API (counted from the tensors copied)
     d2h_bytes = 0        # device->host bytes read back by the API
     timing = False
+    timing_names = None  # None = time every entry; else the set of entry names to time
     events = {}          # name -> list of (start_event, end_event, meta)
 
     @classmethod
-    def reset(cls, timing=False):
-        cls.launches, cls.calls, cls.events, cls.timing = 0, {}, {}, timing
+    def reset(cls, timing=False, names=None):
+        cls.launches, cls.calls, cls.events, cls.timing, cls.timing_names = 0, {}, {}, timing, names
         cls.h2d_bytes = cls.d2h_bytes = 0
 
     @classmethod
@@ -48,7 +49,7 @@ class Profile:
 def _call(h, name, fn, *args, meta=None):
     Profile.launches += KERNELS_PER_CALL[name]
     Profile.calls[name] = Profile.calls.get(name, 0) + 1
-    if Profile.timing:
+    if Profile.timing and (Profile.timing_names is None or name in Profile.timing_names):
         st = torch.cuda.current_stream(h.device)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(st)
