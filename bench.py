@@ -316,16 +316,30 @@ def run_c5(args, rank, world, local_rank):
                       k.tensor_cam.shape[0], k.K, k.image_size) for k in kfs])
 
     def run_all(seqs):
+        """`args.concurrent` sequences at a time, each on its own engine/stream/handle: the host issues keyframe k of every
+        active sequence (step_launch), then completes them (step_finish), so kernels of different sequences overlap."""
         last = None
-        for seq in seqs:
-            eng = FusionEngine(cfg, device=dev, store_capacity=max(65536, 64 * frames))
-            for packed, n, K, size in seq:
-                eng.step(packed, n, K, size)
-            eng.check_status()
-            last = eng
+        S = max(1, args.concurrent)
+        for g0 in range(0, len(seqs), S):
+            group = seqs[g0:g0 + S]
+            engines = pool[: len(group)]
+            for e in engines:
+                e.reset()
+            for k in range(max(len(q) for q in group)):
+                live = [(e, q[k]) for e, q in zip(engines, group) if k < len(q)]
+                for e, (packed, n, K, size) in live:
+                    e.step_launch(packed, n, K, size)
+                for e, _ in live:
+                    e.step_finish()
+            for e in engines:
+                e.check_status()
+            last = engines[-1]
         return last
 
-    run_all([data[0][: max(args.warmup, 3)]])
+    S0 = max(1, args.concurrent)
+    pool = [FusionEngine(cfg, device=dev, store_capacity=max(65536, 64 * frames), private_stream=(S0 > 1))
+            for _ in range(min(S0, len(data)))]
+    run_all([data[i % len(data)][: max(args.warmup, 3) + 10] for i in range(len(pool))])      # warm every engine / handle
     ops.Profile.reset()
     if world > 1:
         torch.distributed.barrier()
@@ -380,6 +394,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = the bench line; c5 = 64 sharded sequences")
     ap.add_argument("--sequences", type=int, default=64)
+    ap.add_argument("--concurrent", type=int, default=8, help="c5: sequences driven concurrently per GPU (streams)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

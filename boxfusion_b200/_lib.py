@@ -98,7 +98,8 @@ def load_library() -> ctypes.CDLL:
 
 
 class Handle:
-    """One bf_handle per CUDA device."""
+    """A bf_handle (device + scratch).  `handle(device)` shares one per device; engines that run concurrently on their
+    own streams create private ones."""
 
     def __init__(self, device: int):
         self.lib = load_library()

@@ -54,7 +54,7 @@ static inline int bf_fail(bf_handle* h, int code, const char* what, const char* 
 // Grow-only scratch.  Growing frees the old block (cudaFree synchronises the device, so no kernel
 // can still be reading it).
 static inline int bf_scratch(bf_handle* h, int slot, size_t bytes, void** out) {
-    if (bytes == 0) bytes = 16;
+    if (bytes < (4u << 20)) bytes = 4u << 20;           // 4 MB floor: maps of a few hundred boxes never regrow (a regrow is a device-wide sync)
     if (h->cap[slot] < bytes) {
         if (h->buf[slot]) BF_CUDA(h, cudaFree(h->buf[slot]));
         h->buf[slot] = nullptr;

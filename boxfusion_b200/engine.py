@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import FusedTable, MapBuffers, StoreBuffers, handle, ptr
+from ._lib import FusedTable, Handle, MapBuffers, StoreBuffers, handle, ptr
 from .box_fusion import _load_pst
 
 _MAP_FIELDS = (("tensor", 6, torch.float32), ("R", 9, torch.float32), ("scores", 1, torch.float32),
@@ -28,6 +28,14 @@ _MAP_FIELDS = (("tensor", 6, torch.float32), ("R", 9, torch.float32), ("scores",
                ("uv", 16, torch.float32), ("valid", 1, torch.float32), ("init_id", 1, torch.int32),
                ("frame_id", 1, torch.int32), ("fl", ops.FUSION_CAP, torch.int32), ("flen", 1, torch.int32))
 _STORE_FIELDS = (("tensor", 6), ("R", 9), ("scores", 1), ("uv", 16), ("pose", 16))
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 def pack_keyframe(tensor_cam, R_cam, scores, pred_boxes, pred_proj_xy, pose) -> np.ndarray:
@@ -43,12 +51,24 @@ def pack_keyframe(tensor_cam, R_cam, scores, pred_boxes, pred_proj_xy, pose) -> 
 
 class FusionEngine:
     def __init__(self, cfg: dict, device="cuda", map_capacity: int = 4096, store_capacity: int = 65536,
-                 fused_capacity: int = 32768, iou_mode: int = ops.IOU_SAMPLED_REF):
+                 fused_capacity: int = 32768, iou_mode: int = ops.IOU_SAMPLED_REF, private_stream: bool = False):
+        """private_stream=True gives the engine its own CUDA stream and its own library handle (scratch), so that
+        several engines - independent sequences - can be driven concurrently from one host thread with
+        step_launch() / step_finish() (bench.py --workload c5)."""
         if cfg["box_fusion"].get("check_valid"):
             raise NotImplementedError("check_valid (box_manager.py:151-166) is not part of the device-resident engine")
         self.cfg = cfg
         self.dev = ops._dev(device if str(device) != "cuda" else None)
-        self.h = handle(self.dev)
+        if map_capacity > 65536:
+            raise ValueError("map_capacity is limited to 65536 rows")
+        if private_stream:
+            self.h = Handle(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+            self.stream = torch.cuda.Stream(self.dev)
+        else:
+            self.h = handle(self.dev)
+            self.stream = None
+        self._evt = torch.cuda.Event()
+        self._pending = None
         self.iou_mode = iou_mode
         self.ncap, self.mcap, self.fcap = int(map_capacity), int(store_capacity), int(fused_capacity)
         d = self.dev
@@ -85,6 +105,18 @@ class FusionEngine:
         self.count = 0        # keyframe counter
         self.last = {"B": 0, "views": 0}
         self.refine_log = None
+        if self.stream is not None:
+            torch.cuda.current_stream(self.dev).synchronize()   # buffers were zero-filled on the creating stream
+
+    def reset(self) -> None:
+        """Start a new sequence in the same buffers (and with the same library handle / scratch)."""
+        assert self._pending is None
+        with self._ctx():
+            self.fused["count"].zero_()
+            self.status.zero_()
+            self.info.zero_()
+        self.N = self.M = self.count = 0
+        self.last = {"B": 0, "views": 0}
 
     def _alloc_map(self):
         d = self.dev
@@ -103,12 +135,25 @@ class FusionEngine:
     # -----------------------------------------------------------------------------------------------------------
     def step(self, packed, n: int, K, image_size) -> None:
         """One keyframe.  `packed`: pack_keyframe() output as a (pinned) CPU tensor, numpy array or CUDA tensor."""
+        self.step_launch(packed, n, K, image_size)
+        self.step_finish()
+
+    def _ctx(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+
+    def step_launch(self, packed, n: int, K, image_size) -> None:
+        """Issue everything of the keyframe up to the 32-byte read-back (asynchronous)."""
+        assert self._pending is None, "step_finish() of the previous keyframe has not been called"
         self.update_intrinsics(image_size, K)                 # demo.py:117-118 (update_K_flag stays False)
         if n == 0:                                            # demo.py:206-212
             self.count += 1
             return
         if self.N + n > self.ncap or self.M + n > self.mcap:
             raise RuntimeError("FusionEngine capacity exceeded (map_capacity / store_capacity)")
+        with self._ctx():
+            self._launch(packed, n, K, image_size)
+
+    def _launch(self, packed, n, K, image_size):
         h, lib, st = self.h, self.h.lib, self.h.stream()
         if isinstance(packed, torch.Tensor):
             if not packed.is_cuda:
@@ -150,13 +195,22 @@ class FusionEngine:
                   ctypes.byref(other["_c"]), ptr(self.info), st)
         self._cur = 1 - self._cur
         mp = self.map
-        # STEP 3: multi-view box fusion (demo.py:304-305)
+        # STEP 3: multi-view box fusion (demo.py:304-305): selection now, refinement after the read-back
         if bf["use"]:
             ops._call(h, "bf_engine_select", lib.bf_engine_select, h.h, ctypes.byref(mp["_c"]), ctypes.byref(self._fused_c),
                       ptr(self.info), ptr(self.todo), ptr(self.offsets), ptr(self.view_index), st)
         self._info_host.copy_(self.info, non_blocking=True)   # the step's only D2H: 32 bytes
-        torch.cuda.current_stream(self.dev).synchronize()
+        self._evt.record(torch.cuda.current_stream(self.dev))
+        self._pending = True
+
+    def step_finish(self) -> None:
+        """Wait for the read-back, then launch the refinement of the selected boxes and its write-back."""
+        if self._pending is None:
+            return
+        self._pending = None
+        self._evt.synchronize()
         ops.Profile.d2h_bytes += 32
+        bf = self.cfg["box_fusion"]
         info = self._info_host.numpy()
         self.N = int(info[1])
         B, SV, maxV = (int(info[2]), int(info[3]), int(info[4])) if bf["use"] else (0, 0, 0)
@@ -164,19 +218,23 @@ class FusionEngine:
             raise RuntimeError(f"FusionEngine: a fusion list has {maxV} views; bf_refine supports {ops.MAX_VIEWS}")
         self.last = {"B": B, "views": SV}
         if B > 0:
-            rcfg = ops.make_refine_cfg(self.cfg, self.K16.reshape(-1), self.H, self.W)
-            rcfg.views_total, rcfg.max_views = SV, maxV
-            ops._call(h, "bf_refine", lib.bf_refine, h.h, ptr(self.pst), self.pst.shape[0], ptr(self.store["tensor"]),
-                      ptr(self.store["R"]), ptr(self.store["scores"]), ptr(self.store["uv"]), ptr(self.store["pose"]), self.M,
-                      ptr(self.offsets), ptr(self.view_index), B, ctypes.byref(rcfg), ptr(self.out), ptr(self.upd), ptr(self.its),
-                      None, ptr(self.status[2:]), st)
-            ops._call(h, "bf_engine_apply", lib.bf_engine_apply, h.h, ctypes.byref(mp["_c"]), ctypes.byref(self._fused_c),
-                      ptr(self.fflag), ptr(self.info), ptr(self.todo), ptr(self.out), ptr(self.upd), ptr(self.status[3:]), st)
+            with self._ctx():
+                h, lib, st, mp = self.h, self.h.lib, self.h.stream(), self.map
+                rcfg = ops.make_refine_cfg(self.cfg, self.K16.reshape(-1), self.H, self.W)
+                rcfg.views_total, rcfg.max_views = SV, maxV
+                ops._call(h, "bf_refine", lib.bf_refine, h.h, ptr(self.pst), self.pst.shape[0], ptr(self.store["tensor"]),
+                          ptr(self.store["R"]), ptr(self.store["scores"]), ptr(self.store["uv"]), ptr(self.store["pose"]), self.M,
+                          ptr(self.offsets), ptr(self.view_index), B, ctypes.byref(rcfg), ptr(self.out), ptr(self.upd), ptr(self.its),
+                          None, ptr(self.status[2:]), st)
+                ops._call(h, "bf_engine_apply", lib.bf_engine_apply, h.h, ctypes.byref(mp["_c"]), ctypes.byref(self._fused_c),
+                          ptr(self.fflag), ptr(self.info), ptr(self.todo), ptr(self.out), ptr(self.upd), ptr(self.status[3:]), st)
             if self.refine_log is not None:
                 self.refine_log.append((B, SV))
         self.count += 1
 
     def check_status(self):
+        if self.stream is not None:
+            self.stream.synchronize()
         s = self.status.cpu().numpy()
         if (s != 0).any():
             raise RuntimeError(f"FusionEngine: capacity error reported by the device (status {s.tolist()})")

@@ -84,3 +84,28 @@ def test_engine_empty_keyframe_and_capacity():
         for k in range(1, 20):
             kf = scene.keyframe(k)
             eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+
+
+def test_concurrent_engines_on_private_streams():
+    """Three independent sequences interleaved from one host thread (step_launch / step_finish on private streams and
+    handles) end in exactly the state they reach when run one after another."""
+    cfg = make_cfg("scannet", pst_path=make_pst(256, seed=3), pst_size=256)
+    scenes = [SyntheticScene(n_objects=60, seed=20 + i, max_det=25, shape="scannet") for i in range(3)]
+    solo = []
+    for sc in scenes:
+        e = FusionEngine(cfg, map_capacity=512, store_capacity=2048, fused_capacity=512)
+        for k in range(15):
+            kf = sc.keyframe(k)
+            e.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+        solo.append(e.snapshot())
+    engines = [FusionEngine(cfg, map_capacity=512, store_capacity=2048, fused_capacity=512, private_stream=True) for _ in scenes]
+    for k in range(15):
+        kfs = [sc.keyframe(k) for sc in scenes]
+        for e, kf in zip(engines, kfs):
+            e.step_launch(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+        for e in engines:
+            e.step_finish()
+    for e, ref in zip(engines, solo):
+        got = e.snapshot()
+        for key in KEYS:
+            assert np.array_equal(_bits(got[key]), _bits(ref[key])), key
