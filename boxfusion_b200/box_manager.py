@@ -47,7 +47,7 @@ class BoxManager:
 
     def add_fusion_ind(self, idx_list):
         if self._fused_n == len(self.already_fusion):        # keep the lookup set in step with the public list
-            self._fused_set.add(tuple(int(x) for x in idx_list))
+            self._fused_set.add(tuple(idx_list))
             self._fused_n += 1
         self.already_fusion.append(copy.deepcopy(idx_list))
 
@@ -55,9 +55,9 @@ class BoxManager:
         """`idx_list in self.already_fusion` (box_manager.py:34-38) through a set of tuples kept in step with the
         public list (rebuilt if a caller edited `already_fusion` directly)."""
         if self._fused_n != len(self.already_fusion):
-            self._fused_set = {tuple(int(x) for x in l) for l in self.already_fusion}
+            self._fused_set = {tuple(l) for l in self.already_fusion}      # int and numpy integers hash/compare alike
             self._fused_n = len(self.already_fusion)
-        return tuple(int(x) for x in idx_list) in self._fused_set
+        return tuple(idx_list) in self._fused_set
 
     def update(self, keep_idx):
         self.fusion_list = [self.fusion_list[i] for i in keep_idx]

@@ -115,9 +115,10 @@ class Instances3D:
         return self._fields[name]
 
     def set(self, name: str, value: Any) -> None:
-        if len(self._fields):
-            assert len(self) == len(value), \
-                "Adding a field of length {} to a Instances3D of length {}".format(len(value), len(self))
+        if self._fields:
+            n_new = value.shape[0] if isinstance(value, (torch.Tensor, np.ndarray)) else len(value)
+            assert len(self) == n_new, \
+                "Adding a field of length {} to a Instances3D of length {}".format(n_new, len(self))
         self._fields[name] = value
 
     def has(self, name: str) -> bool:
@@ -140,7 +141,7 @@ class Instances3D:
 
     def __len__(self) -> int:
         for v in self._fields.values():
-            return v.__len__()
+            return v.shape[0] if isinstance(v, (torch.Tensor, np.ndarray)) else v.__len__()
         raise NotImplementedError("Empty Instances3D does not support __len__!")
 
     def __iter__(self):

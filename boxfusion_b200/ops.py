@@ -65,7 +65,10 @@ def dev_tensor(x, dtype, device) -> torch.Tensor:
     """Contiguous tensor of `dtype` on `device`; host data is copied (and counted), CUDA data is used in place."""
     if not isinstance(x, torch.Tensor):
         x = torch.from_numpy(np.ascontiguousarray(x))
-    if not x.is_cuda:
+    if x.is_cuda:
+        if x.dtype == dtype and x.device == device and x.is_contiguous():
+            return x                                      # the common case: already resident, no torch dispatch at all
+    else:
         Profile.h2d_bytes += x.numel() * x.element_size()
     return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
