@@ -25,6 +25,7 @@ extern "C" int bf_create(int device, bf_handle** out) {
     if (!h) return BF_ERR_INVALID_ARG;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    { const char* t = getenv("BF_REFINE_TIMING"); h->refine_timing = (t && t[0] == '1') ? 1 : 0; }
     *out = h;
     return BF_OK;
 }

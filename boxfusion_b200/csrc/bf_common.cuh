@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/boxfusion_b200.h"
@@ -32,6 +33,7 @@ struct bf_handle {
     int last_refine_cluster;    // cluster size * 1000 + block size of the last bf_refine launch (diagnostic)
     int refine_occ[20];         // cached cudaOccupancyMaxActiveClusters answers per (cluster size, block size)
     long long refine_occ_smem[20];   // dynamic shared memory (+1) the cached answer was computed for
+    int refine_timing;          // BF_REFINE_TIMING=1 in the environment: bf_refine's trace carries per-iteration phase cycle counts (diagnostic)
 };
 
 static inline int bf_fail(bf_handle* h, int code, const char* what, const char* detail) {

@@ -17,290 +17,9 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-struct P2 { float x, y; };
+#include "bf_refine_eval.cuh"
 
-#define BF_CAND_MAX 24          // reference buffer: 36 (box_fusion.py:378), observed maximum 14; overflow is reported, not UB
 #define BF_REFINE_THREADS 512    // upper bound of the block size; the launch picks 128..512 per call
-
-__device__ __forceinline__ float bf_cross(const P2 o, const P2 a, const P2 b) {          // :74-76
-    return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
-}
-
-__device__ __forceinline__ bool bf_after(const P2 a, const P2 b) {                        // sort key of :105-106
-    return a.x > b.x || (a.x == b.x && a.y > b.y);
-}
-
-// Monotone chain over points already sorted by (x,y) (:114-141).  The stack lives in `out`; its top two
-// entries are mirrored in registers so that only a pop touches memory on the critical path.
-// GET(i) yields the i-th sorted point.  Output: lower[:-1] + upper[:-1], exactly the reference's order.
-#define BF_CHAIN(GET, n, out, total, UNROLL)                                                            \
-    {                                                                                             \
-        int nl_ = 0;                                                                              \
-        P2 a_ = {0.f, 0.f}, b_ = {0.f, 0.f};                                                      \
-        _Pragma(UNROLL)                                                                           \
-        for (int i_ = 0; i_ < (n); ++i_) {                                                        \
-            const P2 q_ = GET(i_);                                                                \
-            while (nl_ >= 2 && bf_cross(b_, a_, q_) <= 0) { --nl_; a_ = b_; if (nl_ >= 2) b_ = (out)[nl_ - 2]; } \
-            (out)[nl_] = q_; b_ = a_; a_ = q_; ++nl_;                                             \
-        }                                                                                         \
-        --nl_;                                                                                    \
-        P2* up_ = (out) + nl_;                                                                    \
-        int nu_ = 0;                                                                              \
-        _Pragma(UNROLL)                                                                           \
-        for (int i_ = (n) - 1; i_ >= 0; --i_) {                                                   \
-            const P2 q_ = GET(i_);                                                                \
-            while (nu_ >= 2 && bf_cross(b_, a_, q_) <= 0) { --nu_; a_ = b_; if (nu_ >= 2) b_ = up_[nu_ - 2]; } \
-            up_[nu_] = q_; b_ = a_; a_ = q_; ++nu_;                                               \
-        }                                                                                         \
-        --nu_;                                                                                    \
-        (total) = nl_ + nu_;                                                                      \
-    }
-
-// Hull of exactly 8 points held in registers: 19-comparator sorting network (same order as the
-// reference's exchange sort: equal keys are identical points), then the chain.  out needs 16 slots (the
-// upper chain grows transiently above the kept part of the lower chain).
-__device__ __forceinline__ int bf_hull8(P2 (&p)[8], P2* __restrict__ out) {
-#define BF_CE(i, j) { const bool sw_ = bf_after(p[i], p[j]); const P2 lo_ = sw_ ? p[j] : p[i]; const P2 hi_ = sw_ ? p[i] : p[j]; p[i] = lo_; p[j] = hi_; }
-    BF_CE(0, 1) BF_CE(2, 3) BF_CE(4, 5) BF_CE(6, 7)
-    BF_CE(0, 2) BF_CE(1, 3) BF_CE(4, 6) BF_CE(5, 7)
-    BF_CE(1, 2) BF_CE(5, 6) BF_CE(0, 4) BF_CE(3, 7)
-    BF_CE(1, 5) BF_CE(2, 6)
-    BF_CE(1, 4) BF_CE(3, 6)
-    BF_CE(2, 4) BF_CE(3, 5)
-    BF_CE(3, 4)
-#undef BF_CE
-    int total;
-#define BF_GET8(i) p[i]
-    BF_CHAIN(BF_GET8, 8, out, total, "unroll")
-#undef BF_GET8
-    return total;
-}
-
-// Hull of n points in memory (intersection candidates): insertion sort + chain (:95-145).  out needs 2n slots.
-__device__ __forceinline__ int bf_hull_n(P2* __restrict__ p, int n, P2* __restrict__ out) {
-    if (n == 0) return 0;
-    for (int i = 1; i < n; ++i) {
-        const P2 k = p[i];
-        int j = i - 1;
-        while (j >= 0 && bf_after(p[j], k)) { p[j + 1] = p[j]; --j; }
-        p[j + 1] = k;
-    }
-    int total;
-#define BF_GETN(i) p[i]
-    BF_CHAIN(BF_GETN, n, out, total, "unroll 1")
-#undef BF_GETN
-    return total;
-}
-
-__device__ __forceinline__ float bf_shoelace(const P2* __restrict__ q, int n) {          // :148-156
-    float a = 0.0f;
-    for (int i = 0; i < n; ++i) {
-        const P2 p1 = q[i], p2 = q[(i + 1 == n) ? 0 : i + 1];
-        a += p1.x * p2.y - p2.x * p1.y;
-    }
-    return fabsf(a) * 0.5f;                              // fabs(area)/2.0 is exact either way
-}
-
-// line_intersection (:159-177).  Same doubles, same quotients; the divisions are skipped only where the
-// accept/reject decision cannot depend on their rounding:
-//   n < -1e-7*|den| or n > 1.0000001*|den|  -> the rounded quotient is outside [-1e-8, 1.00000001]
-//   0 <= n <= |den|                          -> the rounded quotient is inside [0, 1]
-// (numerator and denominator are negated together when den < 0: IEEE division is sign-symmetric).
-__device__ __forceinline__ bool bf_seg_intersect(const P2 a1, const P2 a2, const P2 b1, const P2 b2, P2* out) {
-    const double dx1 = a2.x - a1.x, dy1 = a2.y - a1.y;
-    const double dx2 = b2.x - b1.x, dy2 = b2.y - b1.y;
-    const double den = dx1 * dy2 - dy1 * dx2;
-    const double d = fabs(den);
-    if (d < 1e-8) return false;
-    const double e1 = a1.y - b1.y, e2 = b1.x - a1.x;     // float differences widened to double
-    double nt = dx2 * e1 + dy2 * e2;
-    double ns = dx1 * e1 + dy1 * e2;
-    if (den < 0) { nt = -nt; ns = -ns; }
-    const double lo = -1e-7 * d, hi = 1.0000001 * d;
-    if (nt < lo || nt > hi || ns < lo || ns > hi) return false;
-    const double t = nt / d;
-    if (!(nt >= 0 && nt <= d) && !(t >= -1e-8 && t <= 1.00000001)) return false;
-    if (!(ns >= 0 && ns <= d)) {
-        const double s_ = ns / d;
-        if (!(s_ >= -1e-8 && s_ <= 1.00000001)) return false;
-    }
-    out->x = (float)(a1.x + t * dx1);
-    out->y = (float)(a1.y + t * dy1);
-    return true;
-}
-
-// One edge of the even-odd ray cast (:186-196).  x_inters lies within a few ulps of [min(p1.x,p2.x),
-// max(p1.x,p2.x)], so half a pixel of margin decides most edges without the division.
-__device__ __forceinline__ bool bf_ray_edge(const P2 p, const P2 p1, const P2 p2) {
-    if ((p1.y > p.y) == (p2.y > p.y)) return false;
-    if (p.x < fminf(p1.x, p2.x) - 0.5f) return true;
-    if (p.x > fmaxf(p1.x, p2.x) + 0.5f) return false;
-    const float xi = ((p.y - p1.y) * (p2.x - p1.x) / (p2.y - p1.y)) + p1.x;
-    return p.x < xi;
-}
-
-struct bf_view {            // per-view constants staged in shared memory
-    float4 ebb[8];          // bounding box of every edge of the observation hull (xmin, ymin, xmax, ymax)
-    float pose[12];         // rows 0..2 of the camera->world 4x4
-    P2 hull[8];
-    float bb[4];            // bounding box of the observation hull (xmin, ymin, xmax, ymax)
-    int nt;
-    float area_t;
-};
-
-// fill the derived fields of a view once its hull is known
-__device__ __forceinline__ void bf_view_finish(bf_view& vw, const P2* ht) {
-    for (int k = 0; k < 8; ++k) vw.hull[k] = ht[k < vw.nt ? k : 0];
-    vw.area_t = bf_shoelace(ht, vw.nt);
-    float x0 = 1e30f, y0 = 1e30f, x1 = -1e30f, y1 = -1e30f;
-    for (int k = 0; k < vw.nt; ++k) { x0 = fminf(x0, ht[k].x); x1 = fmaxf(x1, ht[k].x); y0 = fminf(y0, ht[k].y); y1 = fmaxf(y1, ht[k].y); }
-    vw.bb[0] = x0; vw.bb[1] = y0; vw.bb[2] = x1; vw.bb[3] = y1;
-    for (int k = 0; k < 8; ++k) {
-        const P2 b1 = vw.hull[k < vw.nt ? k : 0], b2 = vw.hull[(k + 1 < vw.nt) ? k + 1 : 0];
-        vw.ebb[k] = make_float4(fminf(b1.x, b2.x), fminf(b1.y, b2.y), fmaxf(b1.x, b2.x), fmaxf(b1.y, b2.y));
-    }
-}
-
-// IoU of the particle's projected hull (registers, n0 vertices) against the view's observation hull (:380-398).
-// Exact pruning (the decisions below cannot differ from the reference's arithmetic):
-//   * a vertex outside the other polygon's bounding box (0.01 px of slack in x, where the crossing abscissa is a
-//     rounded quantity) is outside the polygon for the even-odd ray cast: no edge straddles its y, or every crossing
-//     lies on one side of it and a closed polygon is crossed an even number of times;
-//   * two edges whose bounding boxes are more than 0.01 px apart cannot intersect: the float64 quotients t, s are
-//     accurate to ~1e-15 (all products of float differences are exact in double), and the accepted parameter range
-//     [-1e-8, 1.00000001] extends an edge by less than 1e-4 px.
-__device__ __forceinline__ float bf_hull_iou(const P2 (&h0)[8], const P2* __restrict__ hl, int n0, const bf_view& vw,
-                                             int* overflow) {
-    const P2* __restrict__ ht = vw.hull;
-    const int nt = vw.nt;
-    P2 cand[BF_CAND_MAX], hi[2 * BF_CAND_MAX];
-    int nc = 0;
-    // bounding box of h0 (hull vertices beyond n0 are ignored)
-    float x0 = h0[0].x, x1 = h0[0].x, y0 = h0[0].y, y1 = h0[0].y;
-#pragma unroll
-    for (int i = 1; i < 8; ++i)
-        if (i < n0) { x0 = fminf(x0, h0[i].x); x1 = fmaxf(x1, h0[i].x); y0 = fminf(y0, h0[i].y); y1 = fmaxf(y1, h0[i].y); }
-    // vertices of h0 inside ht (:210-214)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i < n0) {
-            const P2 q = h0[i];
-            if (q.x >= vw.bb[0] - 0.01f && q.x <= vw.bb[2] + 0.01f && q.y >= vw.bb[1] && q.y <= vw.bb[3]) {
-                bool in = false;
-                for (int j = 0; j < nt; ++j) in ^= bf_ray_edge(q, ht[j], ht[(j + 1 == nt) ? 0 : j + 1]);
-                if (in) { cand[nc] = q; ++nc; }
-            }
-        }
-    }
-    // vertices of ht inside h0 (:215-219)
-    for (int i = 0; i < nt; ++i) {
-        const P2 q = ht[i];
-        if (q.x >= x0 - 0.01f && q.x <= x1 + 0.01f && q.y >= y0 && q.y <= y1) {
-            bool in = false;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < n0) in ^= bf_ray_edge(q, h0[j], (j + 1 < n0) ? h0[(j + 1) & 7] : h0[0]);
-            if (in) { cand[nc] = q; ++nc; }
-        }
-    }
-    // edge x edge intersections (:222-236), two phases so that a warp does not execute the float64 test for every
-    // (i, j) any lane needs: (1) branch-free bounding-box filter -> per-thread bit mask of surviving pairs, bit 8*i+j;
-    // (2) loop over the survivors in the reference's (i, j) order.
-    const float m = 0.01f;
-    unsigned long long pairs = 0ull;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const P2 a1 = h0[i], a2 = (i + 1 < n0) ? h0[(i + 1) & 7] : h0[0];
-        const float ax0 = fminf(a1.x, a2.x) - m, ax1 = fmaxf(a1.x, a2.x) + m, ay0 = fminf(a1.y, a2.y) - m, ay1 = fmaxf(a1.y, a2.y) + m;
-        unsigned row = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 eb = vw.ebb[j];                         // edge j of ht: (xmin, ymin, xmax, ymax)
-            const bool hit = !(ax0 > eb.z || ax1 < eb.x || ay0 > eb.w || ay1 < eb.y) && (j < nt);
-            row |= hit ? (1u << j) : 0u;
-        }
-        if (i < n0) pairs |= (unsigned long long)row << (8 * i);
-    }
-    while (pairs) {
-        const int bit = __ffsll((long long)pairs) - 1;
-        pairs &= pairs - 1;
-        const int i = bit >> 3, j = bit & 7;
-        const P2 a1 = hl[i], a2 = hl[(i + 1 == n0) ? 0 : i + 1];   // same vertices as h0[], read with a dynamic index
-        P2 x;
-        if (bf_seg_intersect(a1, a2, ht[j], ht[(j + 1 == nt) ? 0 : j + 1], &x)) {
-            if (nc < BF_CAND_MAX) cand[nc] = x;
-            ++nc;
-        }
-    }
-    if (nc > BF_CAND_MAX) { *overflow = 1; nc = BF_CAND_MAX; }
-    const int ni = bf_hull_n(cand, nc, hi);
-    const float ai = bf_shoelace(hi, ni);
-    float a0 = 0.0f;                                    // polygon_area(convex_0), vertices in registers
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (i < n0) { const P2 p1 = h0[i], p2 = (i + 1 < n0) ? h0[(i + 1) & 7] : h0[0]; a0 += p1.x * p2.y - p2.x * p1.y; }
-    a0 = fabsf(a0) * 0.5f;
-    const float uni = a0 + vw.area_t - ai;
-    float iou = 0;
-    if (uni > 0) iou = (float)((double)ai / ((double)uni + 0.00001));
-    return iou;
-}
-
-// One (particle, view) term |1 - iou| from the particle's world corners (:345-400).
-__device__ __forceinline__ float bf_eval_view(const float (*c)[3], const bf_view& vw, float fx, float cx, float fy,
-                                              float cy, float img_w, float img_h, int* overflow) {
-    P2 uv[8];
-    const float* ps = vw.pose;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float vx = c[j][0] - ps[3], vy = c[j][1] - ps[7], vz = c[j][2] - ps[11];
-        const float camx = ps[0] * vx + ps[4] * vy + ps[8] * vz;
-        const float camy = ps[1] * vx + ps[5] * vy + ps[9] * vz;
-        const float camz = ps[2] * vx + ps[6] * vy + ps[10] * vz;
-        const float px = ((camx * fx) / camz + cx);
-        const float py = ((camy * fy) / camz + cy);
-        uv[j].x = (px > img_w) ? img_w : (px < 0) ? 0 : px;
-        uv[j].y = (py > img_h) ? img_h : (py < 0) ? 0 : py;
-    }
-    P2 hm[16];
-    const int n0 = bf_hull8(uv, hm);
-    P2 h0[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) h0[k] = hm[k];            // hull vertices back into registers (static indices)
-    const float iou = bf_hull_iou(h0, hm, n0, vw, overflow);
-    return fabsf(1 - iou);
-}
-
-// Particle -> 8 world corners (:289-331).
-__device__ __forceinline__ void bf_particle_corners(const float* box6, const float* pst6, const float* search,
-                                                    const float* rot, float (*c)[3]) {
-    float x3d = box6[0], y3d = box6[1], z3d = box6[2];
-    float w3d = box6[5], h3d = box6[4], l3d = box6[3];
-    x3d = x3d + pst6[0] * search[0];
-    y3d = y3d + pst6[1] * search[1];
-    z3d = z3d + pst6[2] * search[2];
-    w3d = w3d + pst6[5] * search[5];
-    h3d = h3d + pst6[4] * search[4];
-    l3d = l3d + pst6[3] * search[3];
-    const float xyz[3] = {x3d, y3d, z3d};
-    w3d = fmaxf(w3d, 0.01f); h3d = fmaxf(h3d, 0.01f); l3d = fmaxf(l3d, 0.01f);
-    const float hl = l3d / 2, hh = h3d / 2, hw = w3d / 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float vx = ((i & 1) ^ ((i >> 1) & 1)) ? hl : -hl;
-        const float vy = (i & 2) ? hh : -hh;
-        const float vz = (i & 4) ? hw : -hw;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            float acc = 0.0f;
-            acc += rot[j * 3 + 0] * vx;
-            acc += rot[j * 3 + 1] * vy;
-            acc += rot[j * 3 + 2] * vz;
-            acc += xyz[j];
-            c[i][j] = acc;
-        }
-    }
-}
 
 // numpy pairwise_sum for float32 (n <= 128), see oracle/refine_oracle.c
 __device__ float bf_np_pairwise_sum(const float* a, int n) {
@@ -355,7 +74,7 @@ extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
 // One work item = one (view, particle); contributions are stored view-major and summed per particle in ascending
 // view order by the leader (the reference's host order of the atomicAdd sum).
 __global__ void __launch_bounds__(BF_REFINE_THREADS, 1)
-bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float* __restrict__ gcontrib) {
+bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float* __restrict__ gcontrib, int timing) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks();
     const unsigned crank = cluster.block_rank();
@@ -385,15 +104,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
     // ---- stage the views in every CTA: pose rows, observation hull (:367,375) and its area (:389) -------
     for (int v = tid; v < V; v += T) {
         const int m = prm.view_index[v0 + v];
-        bf_view& vw = views[v];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) vw.pose[k] = prm.per_poses[16 * (size_t)m + k];
-        P2 t[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { t[k].x = prm.per_uv[16 * (size_t)m + 2 * k]; t[k].y = prm.per_uv[16 * (size_t)m + 2 * k + 1]; }
-        P2 ht[16];
-        vw.nt = bf_hull8(t, ht);
-        bf_view_finish(vw, ht);
+        bf_view_stage(views[v], prm.per_poses + 16 * (size_t)m, prm.per_uv + 16 * (size_t)m, cfg.img_w, cfg.img_h);
 #pragma unroll
         for (int k = 0; k < 6; ++k) sm->vbox[6 * v + k] = prm.per_xyzlhw[6 * (size_t)m + k];
         sm->vscore[v] = prm.per_scores[m];
@@ -439,6 +150,8 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
     int it = 0;
     cluster.sync();                                      // every CTA's shared memory is initialised
     for (int n = 0; n < cfg.iters; ++n) {
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+        if (timing) tc0 = clock64();
         // ---- evaluate_iou (:413-461): one work item = one (view, particle), spread over the whole cluster ----
         const int items = n_eval * V;
         for (int w = crank * T + tid; w < items; w += C * T) {
@@ -448,10 +161,12 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
             for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
             float c[8][3];
             bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
-            wcontrib[w] = bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
+            wcontrib[w] = bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
         }
         ++it;
+        if (timing) tc1 = clock64();
         cluster.sync();
+        if (timing) tc2 = clock64();
         if (crank == 0) {
             // ---- fitness per particle, views summed in ascending order (:400-401, :454) ---------------------
             for (int p = tid; p < n_eval; p += T) {
@@ -532,12 +247,17 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
                 S->done = (cfg.early_stop && S->fail >= 3) ? 1 : 0;                                   // :713
             }
         }
+        if (timing) tc3 = clock64();
         cluster.sync();                                  // leader state published
         if (crank != 0) {
             if (tid < 6) { S->box6[tid] = l_S->box6[tid]; S->search[tid] = l_S->search[tid]; }
             if (tid == 6) S->done = l_S->done;
         }
         __syncthreads();
+        if (timing && prm.trace && crank == 0 && tid == 0) {   // diagnostic: cycles of {own evaluations, wait for the cluster, leader phase, publish}
+            float* tr = prm.trace + ((size_t)b * cfg.iters + n) * 8;
+            tr[2] = (float)(tc1 - tc0); tr[3] = (float)(tc2 - tc1); tr[4] = (float)(tc3 - tc2); tr[5] = (float)(clock64() - tc3);
+        }
         if (S->done) break;
     }
     if (overflow) atomicExch(&sm->overflow, 1);
@@ -658,7 +378,7 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = bestC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap, max_views, (float*)gscratch);
+        cudaError_t e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap, max_views, (float*)gscratch, h->refine_timing);
         if (e != cudaSuccess) return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
         h->last_refine_cluster = bestC * 1000 + bestT;
     }
@@ -674,13 +394,7 @@ bf_evaluate_kernel(const float* __restrict__ pst, int P, const float* __restrict
     __shared__ bf_refine_state S;
     const int tid = threadIdx.x;
     for (int v = tid; v < V; v += blockDim.x) {
-        bf_view& vw = views[v];
-        for (int k = 0; k < 12; ++k) vw.pose[k] = poses[16 * v + k];
-        P2 t[8], ht[16];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { t[k].x = uv[16 * v + 2 * k]; t[k].y = uv[16 * v + 2 * k + 1]; }
-        vw.nt = bf_hull8(t, ht);
-        bf_view_finish(vw, ht);
+        bf_view_stage(views[v], poses + 16 * v, uv + 16 * v, cfg.img_w, cfg.img_h);
     }
     if (tid == 0) {
         for (int k = 0; k < 6; ++k) { S.box6[k] = box6[k]; S.search[k] = search6[k]; }
@@ -698,7 +412,7 @@ bf_evaluate_kernel(const float* __restrict__ pst, int P, const float* __restrict
             float c[8][3];
             bf_particle_corners(S.box6, pst6, S.search, S.rot, c);
             for (int v = 0; v < V; ++v) {
-                value += bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow);
+                value += bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
                 count += 1;
             }
         }

@@ -141,6 +141,8 @@ int bfo_target_hull(const float* t_c16, float* hull_xy /*[16]*/) {
     return n;
 }
 
+static float iou_points(pt2* uv, pt2* tgt);
+
 /* One (particle, view) evaluation: box_fusion.py:289-398.  Returns iou (float). */
 float bfo_eval_particle_view(const float* box6, const float* t_c16, const float* pst6, const float* rot9,
                              const float* pose16, float fx, float cx, float fy, float cy,
@@ -178,6 +180,18 @@ float bfo_eval_particle_view(const float* box6, const float* t_c16, const float*
     }
     pt2 tgt[8];
     for (int k = 0; k < 8; ++k) { tgt[k].x = t_c16[2 * k]; tgt[k].y = t_c16[2 * k + 1]; }
+    return iou_points(uv, tgt);
+}
+
+/* box_fusion.py:380-398 on two raw 8-point sets (exported for the degenerate-polygon tests of the kernel's
+ * evaluation core: points snapped to a grid, clamped onto the image border, duplicated). */
+float bfo_iou_points(const float* a16, const float* b16) {
+    pt2 a[8], b[8];
+    for (int k = 0; k < 8; ++k) { a[k].x = a16[2 * k]; a[k].y = a16[2 * k + 1]; b[k].x = b16[2 * k]; b[k].y = b16[2 * k + 1]; }
+    return iou_points(a, b);
+}
+
+static float iou_points(pt2* uv, pt2* tgt) {
     pt2 h0[BFO_MAX_HULL], ht[BFO_MAX_HULL], cand[BFO_MAX_CAND], hi[BFO_MAX_HULL];
     const int n0 = hull2d(uv, 8, h0);
     const int nt = hull2d(tgt, 8, ht);
