@@ -13,7 +13,8 @@ from typing import Dict, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libboxfusion_sm100.so")
+# BOXFUSION_B200_LIB: developer knob for kernel-tuning builds of the same library (tools/build_variants.py)
+LIB_PATH = os.environ.get("BOXFUSION_B200_LIB") or os.path.join(_HERE, "lib", "libboxfusion_sm100.so")
 
 BF_OK, BF_ERR_INVALID_ARG, BF_ERR_CUDA, BF_ERR_CAPACITY = 0, -1, -2, -3
 IOU_SAMPLED_REF, IOU_ANALYTIC = 0, 1
@@ -74,6 +75,7 @@ PROTOTYPES = {
     "bf_engine_apply": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bf_detection_filter": (_i32, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _f64, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
+    "bf_refine_last_launch": (_i32, [_vp]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
 }
 

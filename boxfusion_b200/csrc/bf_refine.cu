@@ -20,6 +20,8 @@ namespace cg = cooperative_groups;
 #include "bf_refine_eval.cuh"
 
 #define BF_REFINE_THREADS 512    // upper bound of the block size; the launch picks 128..512 per call
+#define BF_PST_SMEM_MAX 2048      // particle templates up to this size are staged in shared memory
+#define BF_CNT_SLOTS 192          // ceil(P/T) * T/32 + 1 <= (BF_MAX_PARTICLES + BF_REFINE_THREADS) / 32 + 1 = 145
 
 // numpy pairwise_sum for float32 (n <= 128), see oracle/refine_oracle.c
 __device__ float bf_np_pairwise_sum(const float* a, int n) {
@@ -36,6 +38,19 @@ __device__ float bf_np_pairwise_sum(const float* a, int n) {
     float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
     for (; i < n; ++i) res += a[i];
     return res;
+}
+
+// value = sum over views of one particle's contributions in ascending view order (:400-401 with the host's grid order);
+// loads are issued four at a time, the additions stay sequential
+__device__ __forceinline__ float bf_sum_views(const float* __restrict__ c, int stride, int V) {
+    float value = 0.0f;
+    int v = 0;
+    for (; v + 4 <= V; v += 4) {
+        const float t0 = c[(size_t)v * stride], t1 = c[(size_t)(v + 1) * stride], t2 = c[(size_t)(v + 2) * stride], t3 = c[(size_t)(v + 3) * stride];
+        value += t0; value += t1; value += t2; value += t3;
+    }
+    for (; v < V; ++v) value += c[(size_t)v * stride];
+    return value;
 }
 
 struct bf_refine_params {
@@ -63,7 +78,8 @@ struct __align__(16) bf_refine_smem {
     float vscore[BF_MAX_VIEWS];
     float col[3 * BF_MAX_VIEWS];
     int overflow;
-    // followed by: bf_view views[max_views]; float fit[P]; int sel[max_hits]; float terms[8][max_hits]; float contrib[pair_cap]
+    int dbg[2];                           // BF_REFINE_TIMING: max / sum of the cluster's per-warp evaluation cycles
+    // followed by: bf_view views[max_views]; float fit[P]; int cnt[BF_CNT_SLOTS]; float terms[8][max_hits]; float spst[6*pst_cap]; float contrib[pair_cap]
 };
 
 extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
@@ -73,8 +89,16 @@ extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
 // reduces in the reference's order and publishes the new state, two cluster barriers per iteration.
 // One work item = one (view, particle); contributions are stored view-major and summed per particle in ascending
 // view order by the leader (the reference's host order of the atomicAdd sum).
-__global__ void __launch_bounds__(BF_REFINE_THREADS, 1)
-bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float* __restrict__ gcontrib, int timing) {
+//
+// Three instantiations of the same source, chosen per call by the problem size (measured on B200, tools/sweep_shapes.sh):
+//   <false, 512, 1>  latency regime (a handful of boxes, the bench's per-keyframe call): fully unrolled evaluation,
+//                    up to 128 registers, one CTA of up to 512 threads per SM, clusters of 16;
+//   <false, 256, 3>  the call fills the machine a few times over (C1): same code held to 80 registers, three CTAs per SM;
+//   <true,  256, 4>  saturated (C4): compact rolled loops (the unrolled evaluation is ~50 KB of SASS, more than the 32 KB
+//                    L1.5 instruction cache; `no_instruction` was the second largest stall), 64 registers, four CTAs per SM.
+template <bool ROLL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int pst_cap, float* __restrict__ gcontrib, int timing) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks();
     const unsigned crank = cluster.block_rank();
@@ -88,10 +112,11 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
     bf_refine_state* S = &sm->S;
     bf_view* views = (bf_view*)(sm + 1);
     float* fit = (float*)(views + max_views);
-    int* sel = (int*)(fit + prm.P);
-    float* terms = (float*)(sel + cfg.max_hits);          // [8][max_hits] addends of cal_transform
-    float* contrib = terms + 8 * cfg.max_hits;
-    if (tid == 0) sm->overflow = 0;
+    int* cnt = (int*)(fit + prm.P);                       // per (round, warp) hit counts -> exclusive prefixes (+ total)
+    float* terms = (float*)(cnt + BF_CNT_SLOTS);          // [8][max_hits] addends of cal_transform
+    float* spst = terms + 8 * cfg.max_hits;               // particle template staged in shared memory when it fits (pst_cap = P)
+    float* contrib = spst + 6 * pst_cap;
+    if (tid == 0) { sm->overflow = 0; sm->dbg[0] = 0; sm->dbg[1] = 0; }
     if (V < 1 || V > max_views) {                        // flagged in status by bf_check_views_kernel2 (cluster-uniform)
         if (tid == 0 && crank == 0) { prm.out_updated[b] = 0; prm.out_iters[b] = 0; }
         return;
@@ -101,7 +126,9 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
     float* l_contrib = cluster.map_shared_rank(contrib, 0);
     const bf_refine_state* l_S = cluster.map_shared_rank(S, 0);
 
-    // ---- stage the views in every CTA: pose rows, observation hull (:367,375) and its area (:389) -------
+    // ---- stage the particle template and the views in every CTA: pose rows, observation hull (:367,375), area (:389)
+    for (int k = tid; k < 6 * pst_cap; k += T) spst[k] = __ldg(prm.pst + k);
+    const float* __restrict__ pst_src = pst_cap ? spst : prm.pst;
     for (int v = tid; v < V; v += T) {
         const int m = prm.view_index[v0 + v];
         bf_view_stage(views[v], prm.per_poses + 16 * (size_t)m, prm.per_uv + 16 * (size_t)m, cfg.img_w, cfg.img_h);
@@ -150,7 +177,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
     int it = 0;
     cluster.sync();                                      // every CTA's shared memory is initialised
     for (int n = 0; n < cfg.iters; ++n) {
-        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tcA = 0, tcB = 0;
         if (timing) tc0 = clock64();
         // ---- evaluate_iou (:413-461): one work item = one (view, particle), spread over the whole cluster ----
         const int items = n_eval * V;
@@ -158,93 +185,150 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
             const int v = w / n_eval, p = w - v * n_eval;              // view-major: a warp works on one view
             float pst6[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) pst6[k] = __ldg(prm.pst + 6 * (size_t)p + k);
+            for (int k = 0; k < 6; ++k) pst6[k] = pst_src[6 * (size_t)p + k];
             float c[8][3];
             bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
-            wcontrib[w] = bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
+            wcontrib[w] = bf_eval_view<ROLL>(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
         }
         ++it;
-        if (timing) tc1 = clock64();
+        if (timing) {
+            tc1 = clock64();
+            if ((tid & 31) == 0) {
+                int* l_dbg = cluster.map_shared_rank(sm->dbg, 0);
+                atomicMax(l_dbg, (int)(tc1 - tc0)); atomicAdd(l_dbg + 1, (int)((tc1 - tc0) >> 6));
+            }
+        }
         cluster.sync();
         if (timing) tc2 = clock64();
         if (crank == 0) {
-            // ---- fitness per particle, views summed in ascending order (:400-401, :454) ---------------------
-            for (int p = tid; p < n_eval; p += T) {
-                float value = 0.0f, count = 0.0f;
-                for (int v = 0; v < V; ++v) { value += rcontrib[v * n_eval + p]; count += 1; }
-                fit[p] = value / (count + 1e-6f);
+            // ---- fitness per particle, views summed in ascending order (:400-401, :454), and cal_transform's ordered
+            //      selection (:475-535): the first `max_hits` particles j >= 1 with fit[j] < fit[0] in index order.
+            //      Particle j = r*T + tid (conflict-free shared-memory reads); its rank among the hits = hits of earlier
+            //      (round, warp) groups + hits of lower lanes.  Pass 1: fitness + per-group ballot counts; warp 0 turns
+            //      the counts into exclusive prefixes; pass 2: ranks and the eight addends of every selected particle.
+            const int nw = T >> 5, lane = tid & 31, warp = tid >> 5;
+            const int rounds = (prm.P + T - 1) / T;
+            const float denom = (float)V + 1e-6f;                 // count += 1 per view, then count + 1e-6 (:454)
+            const float unlaunched = 0.0f / (0.0f + 1e-6f);       // particles beyond 32*int(pst_size/32)
+            float origin = unlaunched;
+            if (n_eval >= 1) {
+                origin = bf_sum_views(rcontrib, n_eval, V) / denom;
             }
-            for (int p = n_eval + tid; p < prm.P; p += T) fit[p] = 0.0f / (0.0f + 1e-6f);   // never launched
-            __syncthreads();
-            // ---- cal_transform (:475-535): first `max_hits` particles j >= 1 with fit[j] < fit[0], index order
-            const float origin = fit[0];
-            int total = 0;
-            for (int base = 0; base < prm.P && total < cfg.max_hits; base += T) {
-                const int j = base + tid;
-                const bool hit = (j >= 1 && j < prm.P) && (fit[j] < origin);
+            for (int r = 0; r < rounds; ++r) {
+                const int j = r * T + tid;
+                float f = unlaunched;
+                if (j < n_eval) {
+                    f = bf_sum_views(rcontrib + j, n_eval, V) / denom;
+                }
+                if (j < prm.P) fit[j] = f;
+                const bool hit = (j >= 1 && j < prm.P) && (f < origin);
                 const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                const int lane = tid & 31, warp = tid >> 5;
-                if (lane == 0) sm->warp_cnt[warp] = __popc(bal);
-                __syncthreads();
-                int before = total, all = 0;
-                const int nw = T >> 5;
-                for (int w = 0; w < nw; ++w) { const int cw = sm->warp_cnt[w]; if (w < warp) before += cw; all += cw; }
-                const int pos = before + __popc(bal & ((1u << lane) - 1u));
-                if (hit && pos < cfg.max_hits) sel[pos] = j;
-                total += all;
-                __syncthreads();
+                if (lane == 0) cnt[r * nw + warp] = __popc(bal);
             }
-            const int hits = min(total, cfg.max_hits);
-            // the eight addends of every selected particle (6 x PST*w, w, fitness*w) are formed in parallel ...
-            for (int q = tid; q < hits; q += T) {
-                const int j = sel[q];
-                const float w = origin - fit[j];
+            __syncthreads();
+            if (warp == 0) {
+                const int ng = rounds * nw;
+                int carry = 0;
+                for (int base = 0; base < ng; base += 32) {
+                    const int x = (base + lane < ng) ? cnt[base + lane] : 0;
+                    int incl = x;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) terms[k * cfg.max_hits + q] = __ldg(prm.pst + 6 * (size_t)j + k) * w;
-                terms[6 * cfg.max_hits + q] = w;
-                terms[7 * cfg.max_hits + q] = fit[j] * w;
+                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                    if (base + lane < ng) cnt[base + lane] = carry + incl - x;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) cnt[ng] = carry;
             }
             __syncthreads();
-            // ... and accumulated sequentially in index order in float32, like the reference's Python loop (:490-515)
-            if (tid < 8) {
+            const int hits = min(cnt[rounds * nw], cfg.max_hits);
+            for (int r = 0; r < rounds; ++r) {
+                if (cnt[r * nw] >= cfg.max_hits) break;             // block-uniform: every later rank is beyond the cap
+                const int j = r * T + tid;
+                const float f = (j < prm.P) ? fit[j] : 0.0f;
+                const bool hit = (j >= 1 && j < prm.P) && (f < origin);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                const int pos = cnt[r * nw + warp] + __popc(bal & ((1u << lane) - 1u));
+                if (hit && pos < cfg.max_hits) {
+                    const float w = origin - f;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) terms[k * cfg.max_hits + pos] = pst_src[6 * (size_t)j + k] * w;
+                    terms[6 * cfg.max_hits + pos] = w;
+                    terms[7 * cfg.max_hits + pos] = f * w;
+                }
+            }
+            __syncthreads();
+            if (timing) tcA = clock64();
+            // ... accumulated sequentially in index order in float32, like the reference's Python loop (:490-515):
+            // lanes 0..7 of warp 0 own one sum each and hand it to lane 0 by shuffle
+            float acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (warp == 0) {
                 float acc = 0.0f;
-                const float* tq = terms + tid * cfg.max_hits;
-                for (int q = 0; q < hits; ++q) acc += tq[q];
-                S->acc[tid] = acc;
+                if (lane < 8) {
+                    const float* tq = terms + lane * cfg.max_hits;
+                    int q = 0;
+                    for (; q + 8 <= hits; q += 8) {                   // loads batched, additions in index order
+                        float t8[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t8[u] = tq[q + u];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc += t8[u];
+                    }
+                    for (; q < hits; ++q) acc += tq[q];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc8[k] = __shfl_sync(0xffffffffu, acc, k);
             }
-            __syncthreads();
+            if (timing) tcB = clock64();
             if (tid == 0) {
                 int success;
                 float min_iou, mt[6] = {0, 0, 0, 0, 0, 0};
+                float search[6], prev[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { search[k] = S->search[k]; prev[k] = S->prev[k]; }
+                const int previous_success = S->previous_success;
                 if (hits <= 0) { success = 0; min_iou = origin; }
                 else {
                     success = 1;
-                    const float sw = S->acc[6];
-                    min_iou = S->acc[7] / sw;
-                    for (int k = 0; k < 6; ++k) mt[k] = (S->acc[k] / sw) * S->search[k];
+                    const float sw = acc8[6];
+                    min_iou = acc8[7] / sw;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) mt[k] = (acc8[k] / sw) * search[k];
                 }
                 // update_PST (:537-562)
                 const float ms = 1e-3f;
                 float s[6];
+#pragma unroll
                 for (int k = 0; k < 6; ++k) s[k] = fabsf(mt[k]) + ms;
                 float n2 = s[0] * s[0];
+#pragma unroll
                 for (int k = 1; k < 6; ++k) n2 = n2 + s[k] * s[k];
                 const float nrm = sqrtf(n2);
-                for (int k = 3; k < 6; ++k) S->search[k] = cfg.shape_scale * min_iou * (s[k] / nrm) + ms;
-                for (int k = 0; k < 3; ++k) S->search[k] = cfg.center_scale * min_iou * (s[k] / nrm) + ms;
-                if (S->previous_success && success)                                                  // :685-691
-                    for (int k = 0; k < 6; ++k) S->search[k] = beta * S->search[k] + omb * S->prev[k];
+#pragma unroll
+                for (int k = 3; k < 6; ++k) search[k] = cfg.shape_scale * min_iou * (s[k] / nrm) + ms;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) search[k] = cfg.center_scale * min_iou * (s[k] / nrm) + ms;
+                if (previous_success && success) {                                                    // :685-691
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) search[k] = beta * search[k] + omb * prev[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) S->search[k] = search[k];
                 if (success) {                                                                        // :694-706
                     S->need_update = 1; S->previous_success = 1; S->fail = 0;
-                    for (int k = 0; k < 6; ++k) { S->g[k] += (double)mt[k]; S->prev[k] = S->search[k]; }
-                } else { S->fail += 1; S->previous_success = 0; }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { const double g = S->g[k] + (double)mt[k]; S->g[k] = g; S->box6[k] = (float)g; S->prev[k] = search[k]; }
+                    S->done = 0;
+                } else {
+                    const int fail = S->fail + 1;
+                    S->fail = fail; S->previous_success = 0;
+                    S->done = (cfg.early_stop && fail >= 3) ? 1 : 0;                                  // :713
+                }
                 if (prm.trace) {
                     float* tr = prm.trace + ((size_t)b * cfg.iters + n) * 8;
                     tr[0] = (float)success; tr[1] = min_iou;
-                    for (int k = 0; k < 6; ++k) tr[2 + k] = S->search[k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) tr[2 + k] = search[k];
                 }
-                for (int k = 0; k < 6; ++k) S->box6[k] = (float)S->g[k];
-                S->done = (cfg.early_stop && S->fail >= 3) ? 1 : 0;                                   // :713
             }
         }
         if (timing) tc3 = clock64();
@@ -257,6 +341,10 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
         if (timing && prm.trace && crank == 0 && tid == 0) {   // diagnostic: cycles of {own evaluations, wait for the cluster, leader phase, publish}
             float* tr = prm.trace + ((size_t)b * cfg.iters + n) * 8;
             tr[2] = (float)(tc1 - tc0); tr[3] = (float)(tc2 - tc1); tr[4] = (float)(tc3 - tc2); tr[5] = (float)(clock64() - tc3);
+            tr[6] = (float)(tcA - tc2);                                   // leader phase: selection part
+            tr[7] = (float)sm->dbg[0];                                    // slowest warp's evaluation cycles in the cluster
+            tr[1] = (float)sm->dbg[1] * 64.0f / (float)(C * (T >> 5));    // mean warp evaluation cycles (overwrites min_iou in timing mode)
+            sm->dbg[0] = 0; sm->dbg[1] = 0; (void)tcB;
         }
         if (S->done) break;
     }
@@ -279,9 +367,9 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, float*
 
 #define BF_PAIR_CAP 8192       // (view, particle) contributions the leader holds in shared memory: 32 KB
 
-static size_t bf_refine_smem_bytes(int P, int max_hits, int pair_cap, int max_views) {
+static size_t bf_refine_smem_bytes(int P, int max_hits, int pair_cap, int max_views, int pst_cap) {
     return sizeof(bf_refine_smem) + sizeof(bf_view) * (size_t)max_views + sizeof(float) * (size_t)P +
-           sizeof(int) * (size_t)max_hits + sizeof(float) * 8 * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + 16;
+           sizeof(int) * (size_t)BF_CNT_SLOTS + sizeof(float) * 8 * (size_t)max_hits + sizeof(float) * (size_t)pair_cap + sizeof(float) * 6 * (size_t)pst_cap + 16;
 }
 
 __global__ void bf_check_views_kernel(const int32_t* __restrict__ off, int B, int32_t* __restrict__ status) {
@@ -318,8 +406,6 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
     // contributions live in the leader's shared memory only when every box of the call fits BF_PAIR_CAP
     const int n_eval0 = (32 * (cfg->pst_size / 32) < P) ? 32 * (cfg->pst_size / 32) : P;
     const int pair_cap = ((long long)n_eval0 * max_views <= BF_PAIR_CAP) ? n_eval0 * max_views : 0;
-    // rounded up to 8 KB so that the cached occupancy answers below are reused across keyframes
-    const size_t smem = (bf_refine_smem_bytes(P, cfg->max_hits, pair_cap, max_views) + 8191) / 8192 * 8192;
     // global contribution scratch: sum(V) * n_eval floats (only touched by boxes that do not fit shared memory)
     void* gscratch = nullptr;
     {
@@ -328,28 +414,44 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
         int rc = bf_scratch(h, BF_SCRATCH_REFINE, sizeof(float) * (size_t)(views_total * n_eval_h), &gscratch);
         if (rc) return rc;
     }
-    BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BF_CUDA(h, cudaFuncSetAttribute(bf_refine_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    typedef void (*bf_refine_fn)(const bf_refine_params, int, int, int, float*, int);
+    static const bf_refine_fn kernels[3] = {bf_refine_kernel<false, 512, 1>, bf_refine_kernel<false, 256, 3>, bf_refine_kernel<true, 256, 4>};
+    static const int kernel_max_t[3] = {512, 256, 256};
     // Launch shape.  A box's optimiser iteration has items = n_eval * V independent evaluations followed by a short
     // leader phase, so its latency is passes = ceil(items / (C*T)) evaluations; B boxes need waves = ceil(B / clusters
-    // that fit the machine).  Pick the (cluster size C, block size T) that minimises waves * passes, preferring fewer
-    // threads on ties.  Occupancy answers are cached in the handle.
+    // that fit the machine).  Latency regime: pick the (cluster size C, block size T) that minimises waves * passes,
+    // preferring fewer threads on ties; occupancy answers are cached in the handle.
     const int n_eval = n_eval0;
     const long long items = (long long)n_eval * (cfg->views_total > 0 ? (cfg->views_total + B - 1) / B : max_views);
+    // the call returns when its slowest box does: latency is set by the box with the most views (max_views is the caller's bound)
+    const long long items_max = (long long)n_eval * max_views;
     static const int Cs[5] = {16, 8, 4, 2, 1};
     static const int Ts[4] = {512, 384, 256, 128};
-    int bestC = 1, bestT = 256;
+    int bestC = 1, bestT = 256, variant = 0;
     double best_cost = 1e300;
-    // throughput regime (the call alone fills the machine): 256-thread CTAs, two per SM so that one box's leader phase
+    // throughput regimes (the call alone fills the machine): 256-thread CTAs, several per SM so that one box's leader phase
     // and cluster barriers overlap another box's evaluations; cluster just large enough for ~2 items per thread
     const bool saturated = (double)B * (double)items >= (double)h->sm_count * 512.0;
     if (saturated) {
+        variant = ((double)B * (double)items >= (double)h->sm_count * 8192.0) ? 2 : 1;
         bestT = 256;
         while (bestC < 16 && (long long)bestC * bestT * 2 < items) bestC *= 2;
-        while (bestC > 1 && (long long)B * bestC > 4LL * h->sm_count) bestC /= 2;
+        while (bestC > 1 && (long long)B * bestC > 8LL * h->sm_count) bestC /= 2;
         best_cost = 0.0;
     }
-    for (int ci = 0; ci < 5 && !saturated; ++ci)
+    if (h->refine_force_c > 0 && h->refine_force_t > 0) {          // BF_REFINE_SHAPE (tuning sweeps)
+        variant = (h->refine_force_variant >= 0 && h->refine_force_variant < 3) ? h->refine_force_variant : variant;
+        if (h->refine_force_t <= kernel_max_t[variant]) { bestC = h->refine_force_c; bestT = h->refine_force_t; best_cost = 0.0; }
+    }
+    const bf_refine_fn kern = kernels[variant];
+    // the particle template itself in shared memory when it is small (24 KB at P = 1024) - latency regime only: it shortens
+    // the leader phase, but in the throughput regimes the space is worth more as resident CTAs and L1
+    const int pst_cap = (variant == 0 && P <= BF_PST_SMEM_MAX) ? P : 0;
+    // rounded up to 8 KB so that the cached occupancy answers below are reused across keyframes
+    const size_t smem = (bf_refine_smem_bytes(P, cfg->max_hits, pair_cap, max_views, pst_cap) + 8191) / 8192 * 8192;
+    BF_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BF_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    for (int ci = 0; ci < 5 && best_cost > 0.0; ++ci)
         for (int ti = 0; ti < 4; ++ti) {
             const int C = Cs[ci], T = Ts[ti];
             int active = 0;
@@ -362,11 +464,11 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 lc.attrs = at; lc.numAttrs = 1;
-                if (cudaOccupancyMaxActiveClusters(&active, bf_refine_kernel, &lc) != cudaSuccess) { cudaGetLastError(); active = 0; }
+                if (cudaOccupancyMaxActiveClusters(&active, kern, &lc) != cudaSuccess) { cudaGetLastError(); active = 0; }
                 h->refine_occ[slot] = active; h->refine_occ_smem[slot] = (long long)smem + 1;
             }
             if (active < 1) continue;
-            const long long passes = (items + (long long)C * T - 1) / ((long long)C * T);
+            const long long passes = (items_max + (long long)C * T - 1) / ((long long)C * T);
             const long long waves = (B + active - 1) / active;
             const double cost = (double)waves * (double)passes + 1e-6 * C * T;      // ties -> fewer threads
             if (cost < best_cost) { best_cost = cost; bestC = C; bestT = T; }
@@ -378,12 +480,14 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = bestC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&lc, bf_refine_kernel, prm, pair_cap, max_views, (float*)gscratch, h->refine_timing);
+        cudaError_t e = cudaLaunchKernelEx(&lc, kern, prm, pair_cap, max_views, pst_cap, (float*)gscratch, h->refine_timing);
         if (e != cudaSuccess) return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
-        h->last_refine_cluster = bestC * 1000 + bestT;
+        h->last_refine_cluster = variant * 1000000 + bestC * 1000 + bestT;
     }
     return BF_OK;
 }
+
+extern "C" int bf_refine_last_launch(bf_handle* h) { return h ? h->last_refine_cluster : 0; }
 
 // ---- evaluate_iou as a stand-alone entry (tests / diagnostics) -------------------------------------
 __global__ void __launch_bounds__(BF_REFINE_THREADS)
@@ -412,7 +516,7 @@ bf_evaluate_kernel(const float* __restrict__ pst, int P, const float* __restrict
             float c[8][3];
             bf_particle_corners(S.box6, pst6, S.search, S.rot, c);
             for (int v = 0; v < V; ++v) {
-                value += bf_eval_view(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
+                value += bf_eval_view<false>(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
                 count += 1;
             }
         }

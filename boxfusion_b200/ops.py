@@ -238,6 +238,13 @@ def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, 
     return out, upd, its, trace, status
 
 
+def last_refine_launch(device=None) -> dict:
+    """Diagnostic: kernel instantiation / cluster size / block size of the handle's last bf_refine launch."""
+    h = handle(device)
+    v = int(h.lib.bf_refine_last_launch(h.h))
+    return {"variant": ("latency", "mid", "saturated")[v // 1000000], "cluster": (v % 1000000) // 1000, "threads": v % 1000}
+
+
 def evaluate_iou(pst, box6, rot9, uv, poses, search6, rcfg: RefineCfg) -> torch.Tensor:
     """BoxFusion.evaluate_iou (box_fusion.py:413-461) -> fitness[P] float32 on the device."""
     dev = _pick_device(pst, uv)

@@ -135,6 +135,10 @@ int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,
               float* out_xyzlhw /*[B,6]*/, int32_t* out_updated /*[B]*/, int32_t* out_iters /*[B]*/,
               float* trace /*[B,iters,8] or NULL: success,min_iou,search[6]*/, int32_t* status /*[1]*/, void* stream);
 
+/* Diagnostic: how the last bf_refine call of this handle was launched: kernel instantiation * 1000000 (0 = latency
+ * regime, 1 = mid, 2 = saturated / compact code) + cluster size * 1000 + block size.  No reference counterpart. */
+int bf_refine_last_launch(bf_handle* h);
+
 /* BoxFusion.evaluate_iou (box_fusion.py:413-461): one fitness vector for one box (test/diagnostic entry). */
 int bf_evaluate_iou(bf_handle* h, const float* pst /*[P,6]*/, int P, const float* box6 /*[6]*/, const float* rot9,
                     const float* uv /*[V,16]*/, const float* poses /*[V,16]*/, int V, const float* search6,

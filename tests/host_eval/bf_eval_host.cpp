@@ -6,12 +6,13 @@
 
 extern "C" {
 
+// `rolled` selects the kernel's code-size variant (compact rolled loops for the saturated regime, or fully unrolled).
 // bf_evaluate_kernel's loops on the host: fitness[P] of one box against V views (box_fusion.py:413-461).
 // stats[0] += evaluations, stats[1] += evaluations that needed at least one exact fallback test,
 // stats[2] += fallback tests, stats[3] |= candidate overflow.
 void bfh_evaluate(const float* box6, const float* t_c /*[V,16]*/, const float* pst /*[P,6]*/, int P, int n_eval,
                   const float* rot9, const float* poses /*[V,16]*/, int V, float fx, float cx, float fy, float cy,
-                  const float* search6, float img_h, float img_w, float* fitness /*[P]*/, long long* stats /*[4]*/) {
+                  const float* search6, float img_h, float img_w, float* fitness /*[P]*/, long long* stats /*[4]*/, int rolled) {
     bf_view* views = new bf_view[V];
     for (int v = 0; v < V; ++v) bf_view_stage(views[v], poses + 16 * v, t_c + 16 * v, img_w, img_h);
     long long n_ev = 0, n_fb_ev = 0, n_fb = 0;
@@ -24,7 +25,8 @@ void bfh_evaluate(const float* box6, const float* t_c /*[V,16]*/, const float* p
             bf_particle_corners(box6, pst + 6 * p, search6, rot9, c);
             for (int v = 0; v < V; ++v) {
                 int over = 0, fb = 0;
-                value += bf_eval_view(c, views[v], fx, cx, fy, cy, img_w, img_h, &over, &fb);
+                value += rolled ? bf_eval_view<true>(c, views[v], fx, cx, fy, cy, img_w, img_h, &over, &fb)
+                                : bf_eval_view<false>(c, views[v], fx, cx, fy, cy, img_w, img_h, &over, &fb);
                 count += 1;
                 n_ev += 1; n_fb_ev += (fb > 0); n_fb += fb; any_over |= over;
             }
@@ -37,7 +39,7 @@ void bfh_evaluate(const float* box6, const float* t_c /*[V,16]*/, const float* p
 
 // box_fusion.py:380-398 on two raw 8-point sets (a = particle side, b = observation side), through the same
 // bf_hull8 / bf_view_finish / bf_hull_iou path the kernel takes.
-float bfh_iou_points(const float* a16, const float* b16, float img_w, float img_h, int* fallbacks, int* overflow) {
+float bfh_iou_points(const float* a16, const float* b16, float img_w, float img_h, int* fallbacks, int* overflow, int rolled) {
     bf_view vw;
     float pose[16] = {0};
     bf_view_stage(vw, pose, b16, img_w, img_h);
@@ -45,11 +47,11 @@ float bfh_iou_points(const float* a16, const float* b16, float img_w, float img_
     for (int k = 0; k < 8; ++k) { uv[k].x = a16[2 * k]; uv[k].y = a16[2 * k + 1]; }
     P2 hm[16];
     for (int k = 0; k < 16; ++k) { hm[k].x = 0.f; hm[k].y = 0.f; }
-    const int n0 = bf_hull8(uv, hm);
+    const int n0 = rolled ? bf_hull8<true>(uv, hm) : bf_hull8<false>(uv, hm);
     P2 h0[8];
     for (int k = 0; k < 8; ++k) h0[k] = hm[k];
     int fb = 0, over = 0;
-    const float iou = bf_hull_iou(h0, hm, n0, vw, &over, &fb);
+    const float iou = rolled ? bf_hull_iou<true>(h0, hm, n0, vw, &over, &fb) : bf_hull_iou<false>(h0, hm, n0, vw, &over, &fb);
     if (fallbacks) *fallbacks = fb;
     if (overflow) *overflow = over;
     return iou;

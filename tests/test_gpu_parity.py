@@ -270,8 +270,12 @@ def test_refine_matches_reference_golden(golden_dir, V):
     assert bm.already_fusion == bm.fusion_list
 
 
-@pytest.mark.parametrize("B,V,P,pst_size", [(12, 8, 512, 512), (6, 32, 1024, 1024), (5, 4, 500, 500), (3, 64, 256, 256)])
-def test_refine_matches_c_oracle(B, V, P, pst_size):
+@pytest.mark.parametrize("B,V,P,pst_size,variant", [(12, 8, 512, 512, "latency"), (6, 32, 1024, 1024, None), (5, 4, 500, 500, "latency"),
+                                                    (3, 64, 256, 256, None),
+                                                    # the other two instantiations of bf_refine_kernel (chosen by problem size)
+                                                    (24, 8, 512, 512, "mid"), (40, 16, 2048, 2048, "saturated")])
+def test_refine_matches_c_oracle(B, V, P, pst_size, variant):
+    ro.set_threads(os.cpu_count() or 1)          # the oracle's particles are independent: threads only change who computes what
     prob = refine_problem(B, V, seed=B * 100 + V)
     W, H = prob["size"]
     pst = make_pst(P, seed=1)
@@ -285,8 +289,10 @@ def test_refine_matches_c_oracle(B, V, P, pst_size):
     idx = np.arange(B * V, dtype=np.int32)
     out, upd, its, trace, status = ops.refine(pst, prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 9),
                                               prob["scores"].reshape(-1), proj, prob["poses"].reshape(-1, 16), off, idx,
-                                              rcfg, want_trace=True)
+                                              rcfg, want_trace=True, max_views=V)
     assert int(status.item()) == 0
+    if variant is not None:
+        assert ops.last_refine_launch()["variant"] == variant
     out, upd, its, trace = out.cpu().numpy(), upd.cpu().numpy(), its.cpu().numpy(), trace.cpu().numpy()
     cs = ro.make_cfg_struct(cfg, H, W)
     for b in range(B):

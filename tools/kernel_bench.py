@@ -52,11 +52,11 @@ def refine_case(name, B, V, P, early_stop, peak):
     res = {}
 
     def run():
-        res["out"] = ops.refine(pst, t, R, s, uv, po, off, idx, rcfg)
+        res["out"] = ops.refine(pst, t, R, s, uv, po, off, idx, rcfg, max_views=V)   # like BoxFusion.boxfusion / FusionEngine
     med, best = timeit(run)
     its = res["out"][2].cpu().numpy()
     evals = float(its.sum()) * P * V
-    print(json.dumps({"case": name, "B": B, "V": V, "P": P, "early_stop": early_stop, "ms": round(med, 4), "ms_best": round(best, 4),
+    print(json.dumps({"case": name, "B": B, "V": V, "P": P, "early_stop": early_stop, "launch": ops.last_refine_launch(), "ms": round(med, 4), "ms_best": round(best, 4),
                       "iters_mean": round(float(its.mean()), 2), "evals": evals, "evals_per_s": round(evals / (med * 1e-3), 1),
                       "ms_per_iteration": round(med / float(its.max()), 4),
                       "fp32_tflops_algorithmic": round(evals * FLOP_PER_EVAL / (med * 1e-3) / 1e12, 3),
@@ -107,6 +107,8 @@ def main():
         refine_case("C2-like refine launch (7 boxes x 6 views x 1024 particles)", 7, 6, 1024, True, peak)
     if "c1" in cases:
         refine_case("C1 refine (35 boxes x 8 views x 512 particles)", 35, 8, 512, True, peak)
+    if "c4f" in cases:    # forced-iteration C4 only (tuning sweeps)
+        refine_case("C4 refine forced 20 iterations", 128, 32, 4096, False, peak)
     if "c4" in cases:
         refine_case("C4 refine forced 20 iterations", 128, 32, 4096, False, peak)
         refine_case("C4 refine early stop", 128, 32, 4096, True, peak)

@@ -28,15 +28,15 @@ def case(name, B, V, P):
     idx = torch.arange(B * V, dtype=torch.int32, device=dev)
     rcfg = ops.make_refine_cfg(cfg, K16.reshape(-1), H, W)
     for _ in range(3):
-        out = ops.refine(pst, t, R, s, uv, po, off, idx, rcfg, want_trace=True)
+        out = ops.refine(pst, t, R, s, uv, po, off, idx, rcfg, want_trace=True, max_views=V)
     torch.cuda.synchronize()
     its = out[2].cpu().numpy()
     tr = out[3].cpu().numpy().reshape(B, -1, 8)
-    rows = np.concatenate([tr[b, :its[b], 2:6] for b in range(B)], 0)
+    rows = np.concatenate([tr[b, :its[b], 1:8] for b in range(B)], 0)[:, [1, 2, 3, 4, 5, 6, 0]]
     m = rows.mean(0)
     print(json.dumps({"case": name, "launch": ops.last_refine_launch() if hasattr(ops, "last_refine_launch") else None,
                       "iters_mean": float(its.mean()),
-                      "cycles_mean": {"own_evals": float(m[0]), "wait_cluster": float(m[1]), "leader": float(m[2]), "publish": float(m[3])},
+                      "cycles_mean": {"own_evals": float(m[0]), "wait_cluster": float(m[1]), "leader": float(m[2]), "publish": float(m[3]), "leader_select": float(m[4]), "warp_eval_max": float(m[5]), "warp_eval_mean": float(m[6])},
                       "cycles_p90": [float(x) for x in np.percentile(rows, 90, axis=0)]}))
 
 

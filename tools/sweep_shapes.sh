@@ -1,0 +1,16 @@
+#!/bin/bash
+# tuning sweep: kernel variant x forced launch shape, C4 / C1 kernel-level cases
+for v in "$@"; do
+  for shape in auto 1,256 2,256 4,256 8,256 2,128 4,128 8,128; do
+    if [ "$shape" = auto ]; then unset BF_REFINE_SHAPE; else export BF_REFINE_SHAPE=$shape; fi
+    BOXFUSION_B200_LIB=$PWD/boxfusion_b200/lib/variants/lib_$v.so python tools/kernel_bench.py --cases c1,c4f 2>&1 | python -c "
+import sys,json
+o=[]
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except: continue
+    if 'case' in d: o.append('%s %.3f' % (d['case'][:9], d['ms']))
+print('$v', '$shape', ' | '.join(o))
+"
+  done
+done
