@@ -25,7 +25,7 @@ extern "C" int bf_create(int device, bf_handle** out) {
     if (!h) return BF_ERR_INVALID_ARG;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    { const char* t = getenv("BF_REFINE_TIMING"); h->refine_timing = (t && t[0] == '1') ? 1 : 0; }
+    { const char* t = getenv("BF_REFINE_TIMING"); h->refine_timing = (t && (t[0] == '1' || t[0] == '2')) ? (t[0] - '0') : 0; }
     { const char* t = getenv("BF_REFINE_SHAPE"); h->refine_force_variant = -1; if (t) sscanf(t, "%d,%d,%d", &h->refine_force_c, &h->refine_force_t, &h->refine_force_variant); }
     *out = h;
     return BF_OK;

@@ -41,15 +41,18 @@ __device__ float bf_np_pairwise_sum(const float* a, int n) {
 }
 
 // value = sum over views of one particle's contributions in ascending view order (:400-401 with the host's grid order);
-// loads are issued four at a time, the additions stay sequential
+// loads are issued four at a time, the additions stay sequential.  32-bit indexing and a rolled loop on purpose: the
+// leader phase is short and runs once per iteration, its cost is instruction fetch more than arithmetic.
 __device__ __forceinline__ float bf_sum_views(const float* __restrict__ c, int stride, int V) {
     float value = 0.0f;
     int v = 0;
+#pragma unroll 1
     for (; v + 4 <= V; v += 4) {
-        const float t0 = c[(size_t)v * stride], t1 = c[(size_t)(v + 1) * stride], t2 = c[(size_t)(v + 2) * stride], t3 = c[(size_t)(v + 3) * stride];
+        const float t0 = c[v * stride], t1 = c[(v + 1) * stride], t2 = c[(v + 2) * stride], t3 = c[(v + 3) * stride];
         value += t0; value += t1; value += t2; value += t3;
     }
-    for (; v < V; ++v) value += c[(size_t)v * stride];
+#pragma unroll 1
+    for (; v < V; ++v) value += c[v * stride];
     return value;
 }
 
@@ -128,7 +131,6 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
 
     // ---- stage the particle template and the views in every CTA: pose rows, observation hull (:367,375), area (:389)
     for (int k = tid; k < 6 * pst_cap; k += T) spst[k] = __ldg(prm.pst + k);
-    const float* __restrict__ pst_src = pst_cap ? spst : prm.pst;
     for (int v = tid; v < V; v += T) {
         const int m = prm.view_index[v0 + v];
         bf_view_stage(views[v], prm.per_poses + 16 * (size_t)m, prm.per_uv + 16 * (size_t)m, cfg.img_w, cfg.img_h);
@@ -171,13 +173,12 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
     // memory (written through DSMEM); large ones (C4: 4096 x 32) use an L2-resident global scratch slab of this box.
     const bool in_smem = (long long)n_eval * V <= (long long)pair_cap;
     float* wcontrib = in_smem ? l_contrib : gcontrib + (size_t)v0 * n_eval;        // where this CTA writes
-    const float* rcontrib = in_smem ? contrib : gcontrib + (size_t)v0 * n_eval;    // where the leader reads
     const float beta = (float)cfg.beta, omb = (float)(1.0 - cfg.beta);
     int overflow = 0;
     int it = 0;
     cluster.sync();                                      // every CTA's shared memory is initialised
     for (int n = 0; n < cfg.iters; ++n) {
-        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tcA = 0, tcB = 0;
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tcA = 0, tcB = 0, tcP1 = 0, tcP2 = 0;
         if (timing) tc0 = clock64();
         // ---- evaluate_iou (:413-461): one work item = one (view, particle), spread over the whole cluster ----
         const int items = n_eval * V;
@@ -185,7 +186,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
             const int v = w / n_eval, p = w - v * n_eval;              // view-major: a warp works on one view
             float pst6[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) pst6[k] = pst_src[6 * (size_t)p + k];
+            for (int k = 0; k < 6; ++k) pst6[k] = pst_cap ? spst[6 * p + k] : __ldg(prm.pst + 6 * p + k);
             float c[8][3];
             bf_particle_corners(S->box6, pst6, S->search, S->rot, c);
             wcontrib[w] = bf_eval_view<ROLL>(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
@@ -212,13 +213,14 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
             const float unlaunched = 0.0f / (0.0f + 1e-6f);       // particles beyond 32*int(pst_size/32)
             float origin = unlaunched;
             if (n_eval >= 1) {
-                origin = bf_sum_views(rcontrib, n_eval, V) / denom;
+                origin = (in_smem ? bf_sum_views(contrib, n_eval, V) : bf_sum_views(gcontrib + (size_t)v0 * n_eval, n_eval, V)) / denom;
             }
+#pragma unroll 1
             for (int r = 0; r < rounds; ++r) {
                 const int j = r * T + tid;
                 float f = unlaunched;
                 if (j < n_eval) {
-                    f = bf_sum_views(rcontrib + j, n_eval, V) / denom;
+                    f = (in_smem ? bf_sum_views(contrib + j, n_eval, V) : bf_sum_views(gcontrib + (size_t)v0 * n_eval + j, n_eval, V)) / denom;
                 }
                 if (j < prm.P) fit[j] = f;
                 const bool hit = (j >= 1 && j < prm.P) && (f < origin);
@@ -226,9 +228,11 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
                 if (lane == 0) cnt[r * nw + warp] = __popc(bal);
             }
             __syncthreads();
+            if (timing) tcP1 = clock64();
             if (warp == 0) {
                 const int ng = rounds * nw;
                 int carry = 0;
+#pragma unroll 1
                 for (int base = 0; base < ng; base += 32) {
                     const int x = (base + lane < ng) ? cnt[base + lane] : 0;
                     int incl = x;
@@ -240,7 +244,9 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
                 if (lane == 0) cnt[ng] = carry;
             }
             __syncthreads();
+            if (timing) tcP2 = clock64();
             const int hits = min(cnt[rounds * nw], cfg.max_hits);
+#pragma unroll 1
             for (int r = 0; r < rounds; ++r) {
                 if (cnt[r * nw] >= cfg.max_hits) break;             // block-uniform: every later rank is beyond the cap
                 const int j = r * T + tid;
@@ -251,7 +257,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
                 if (hit && pos < cfg.max_hits) {
                     const float w = origin - f;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) terms[k * cfg.max_hits + pos] = pst_src[6 * (size_t)j + k] * w;
+                    for (int k = 0; k < 6; ++k) terms[k * cfg.max_hits + pos] = (pst_cap ? spst[6 * j + k] : __ldg(prm.pst + 6 * j + k)) * w;
                     terms[6 * cfg.max_hits + pos] = w;
                     terms[7 * cfg.max_hits + pos] = f * w;
                 }
@@ -266,6 +272,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
                 if (lane < 8) {
                     const float* tq = terms + lane * cfg.max_hits;
                     int q = 0;
+#pragma unroll 1
                     for (; q + 8 <= hits; q += 8) {                   // loads batched, additions in index order
                         float t8[8];
 #pragma unroll
@@ -273,6 +280,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
 #pragma unroll
                         for (int u = 0; u < 8; ++u) acc += t8[u];
                     }
+#pragma unroll 1
                     for (; q < hits; ++q) acc += tq[q];
                 }
 #pragma unroll
@@ -342,6 +350,7 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
             float* tr = prm.trace + ((size_t)b * cfg.iters + n) * 8;
             tr[2] = (float)(tc1 - tc0); tr[3] = (float)(tc2 - tc1); tr[4] = (float)(tc3 - tc2); tr[5] = (float)(clock64() - tc3);
             tr[6] = (float)(tcA - tc2);                                   // leader phase: selection part
+            if (timing == 2) { tr[2] = (float)(tcP1 - tc2); tr[3] = (float)(tcP2 - tcP1); tr[5] = (float)(tcA - tcP2); }   // finer split of the selection
             tr[7] = (float)sm->dbg[0];                                    // slowest warp's evaluation cycles in the cluster
             tr[1] = (float)sm->dbg[1] * 64.0f / (float)(C * (T >> 5));    // mean warp evaluation cycles (overwrites min_iou in timing mode)
             sm->dbg[0] = 0; sm->dbg[1] = 0; (void)tcB;
@@ -468,8 +477,8 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
                 h->refine_occ[slot] = active; h->refine_occ_smem[slot] = (long long)smem + 1;
             }
             if (active < 1) continue;
-            const long long passes = (items_max + (long long)C * T - 1) / ((long long)C * T);
             const long long waves = (B + active - 1) / active;
+            const long long passes = (items_max + (long long)C * T - 1) / ((long long)C * T);
             const double cost = (double)waves * (double)passes + 1e-6 * C * T;      // ties -> fewer threads
             if (cost < best_cost) { best_cost = cost; bestC = C; bestT = T; }
         }

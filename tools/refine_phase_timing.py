@@ -4,7 +4,7 @@ import json
 import os
 import sys
 
-os.environ["BF_REFINE_TIMING"] = "1"
+os.environ.setdefault("BF_REFINE_TIMING", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
