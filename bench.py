@@ -258,7 +258,7 @@ def run_ours(args, rank, world, local_rank):
         hbm_ach = tot_ev * BYTES_PER_EVAL / (tot_ms * 1e-3) / 1e9
         # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of this command
         traffic, tsrc = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_v11_refine_bench_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1_v12_refine_bench_traffic.json")
         if os.path.isfile(tpath):
             tj = json.load(open(tpath))
             traffic, tsrc = round(tj["dram_bytes_per_launch_mean"]), tj["source"]

@@ -41,15 +41,20 @@ __device__ float bf_np_pairwise_sum(const float* a, int n) {
 }
 
 // value = sum over views of one particle's contributions in ascending view order (:400-401 with the host's grid order);
-// loads are issued four at a time, the additions stay sequential.  32-bit indexing and a rolled loop on purpose: the
-// leader phase is short and runs once per iteration, its cost is instruction fetch more than arithmetic.
+// loads are issued U at a time (4 from shared memory, 16 from the L2-resident global slab, whose latency is what the
+// saturated regime's leader phase waits for), the additions stay sequential.  32-bit indexing and rolled loops on
+// purpose: the leader phase is short and runs once per iteration, its cost is instruction fetch more than arithmetic.
+template <int U>
 __device__ __forceinline__ float bf_sum_views(const float* __restrict__ c, int stride, int V) {
     float value = 0.0f;
     int v = 0;
 #pragma unroll 1
-    for (; v + 4 <= V; v += 4) {
-        const float t0 = c[v * stride], t1 = c[(v + 1) * stride], t2 = c[(v + 2) * stride], t3 = c[(v + 3) * stride];
-        value += t0; value += t1; value += t2; value += t3;
+    for (; v + U <= V; v += U) {
+        float t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = c[(v + u) * stride];
+#pragma unroll
+        for (int u = 0; u < U; ++u) value += t[u];
     }
 #pragma unroll 1
     for (; v < V; ++v) value += c[v * stride];
@@ -213,14 +218,14 @@ bf_refine_kernel(const bf_refine_params prm, int pair_cap, int max_views, int ps
             const float unlaunched = 0.0f / (0.0f + 1e-6f);       // particles beyond 32*int(pst_size/32)
             float origin = unlaunched;
             if (n_eval >= 1) {
-                origin = (in_smem ? bf_sum_views(contrib, n_eval, V) : bf_sum_views(gcontrib + (size_t)v0 * n_eval, n_eval, V)) / denom;
+                origin = (in_smem ? bf_sum_views<4>(contrib, n_eval, V) : bf_sum_views<16>(gcontrib + (size_t)v0 * n_eval, n_eval, V)) / denom;
             }
 #pragma unroll 1
             for (int r = 0; r < rounds; ++r) {
                 const int j = r * T + tid;
                 float f = unlaunched;
                 if (j < n_eval) {
-                    f = (in_smem ? bf_sum_views(contrib + j, n_eval, V) : bf_sum_views(gcontrib + (size_t)v0 * n_eval + j, n_eval, V)) / denom;
+                    f = (in_smem ? bf_sum_views<4>(contrib + j, n_eval, V) : bf_sum_views<16>(gcontrib + (size_t)v0 * n_eval + j, n_eval, V)) / denom;
                 }
                 if (j < prm.P) fit[j] = f;
                 const bool hit = (j >= 1 && j < prm.P) && (f < origin);
