@@ -14,6 +14,52 @@ __global__ void bf_rank_kernel(const int32_t* __restrict__ order, int N, int32_t
     if (r < N) rank[order[r]] = r;
 }
 
+// ---- score order of nms_3d (instances.py:52) ---------------------------------------------------------------------
+// 64-bit keys (descending score, ascending index) sorted ascending by a bitonic network in shared memory.
+#define BF_ORDER_MAX 4096
+__global__ void __launch_bounds__(1024)
+bf_score_order_kernel(const float* __restrict__ scores, int N, int n_pad, int32_t* __restrict__ order) {
+    extern __shared__ unsigned long long bf_keys[];
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        unsigned long long k = ~0ull;                                   // padding sorts last
+        if (i < N) {
+            float f = scores[i];
+            unsigned u;
+            if (f != f) u = 0xffffffffu;                                // NaN: greater than everything (torch's order)
+            else {
+                if (f == 0.0f) f = 0.0f;                                // -0 == +0
+                const unsigned b = __float_as_uint(f);
+                u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);         // monotone float -> unsigned
+            }
+            k = ((unsigned long long)(~u) << 32) | (unsigned)i;        // descending score, then ascending index
+        }
+        bf_keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n_pad; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = bf_keys[lo], b = bf_keys[hi];
+                if ((a > b) == up) { bf_keys[lo] = b; bf_keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = (int32_t)(bf_keys[i] & 0xffffffffull);
+}
+
+extern "C" int bf_score_order(bf_handle* h, const float* scores, int N, int32_t* order, void* stream) {
+    if (!h || N < 0 || N > BF_ORDER_MAX || (N > 0 && (!scores || !order))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_score_order", "bad argument");
+    if (N == 0) return BF_OK;
+    int n_pad = 2;
+    while (n_pad < N) n_pad <<= 1;
+    const int threads = n_pad / 2 < 1024 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 1024;
+    bf_score_order_kernel<<<1, threads, sizeof(unsigned long long) * (size_t)n_pad, (cudaStream_t)stream>>>(scores, N, n_pad, order);
+    BF_LAUNCH_CHECK(h, "bf_score_order_kernel");
+    return BF_OK;
+}
+
 // box_manager.py:188-215 with the test of :55 / :71
 __device__ __forceinline__ bool bf_views_differ(const float* __restrict__ p1, const float* __restrict__ p2,
                                                 float translation_gap, float rotation_gap, bool use_center,

@@ -59,7 +59,7 @@ def nms_3d(instance_lists, box_manager, boxes, scores, init_id, cam_poses, box_s
 def _nms_device(instance_lists, box_manager, corners, centers, scores, init_id, cam_poses, iou_threshold, dev):
     n = corners.shape[0]
     s = ops.dev_tensor(scores, torch.float32, dev).reshape(-1)
-    order = torch.argsort(s, descending=True, stable=True).to(torch.int32)         # scores.argsort()[::-1]
+    order = ops.score_order(s)                                                     # scores.argsort()[::-1], stable (bf_score_order)
     iid = ops.dev_tensor(init_id, torch.int64, dev).to(torch.int32).reshape(-1)
     poses = ops.dev_tensor(cam_poses, torch.float32, dev).reshape(-1, 16)
     fl_h, ln_h, flag_h = box_manager.pack_lists(n)

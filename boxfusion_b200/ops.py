@@ -22,7 +22,7 @@ MAX_VIEWS = 64
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
                     "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1,
                     "bf_engine_ingest": 1, "bf_engine_corr": 1, "bf_engine_compact": 2, "bf_engine_select": 1,
-                    "bf_engine_apply": 1, "bf_detection_filter": 1}
+                    "bf_engine_apply": 1, "bf_detection_filter": 1, "bf_score_order": 1}
 
 
 class Profile:
@@ -236,6 +236,22 @@ def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, 
                             ptr(off), ptr(idx), B, ctypes.byref(rcfg), ptr(out), ptr(upd), ptr(its), ptr(trace),
                             ptr(status), h.stream())
     return out, upd, its, trace, status
+
+
+ORDER_MAX = 4096
+
+
+def score_order(scores) -> torch.Tensor:
+    """`scores.argsort()[::-1]` of nms_3d (instances.py:52) as a stable descending sort on the device -> int32 [N]."""
+    dev = _pick_device(scores)
+    s = dev_tensor(scores, torch.float32, dev).reshape(-1)
+    n = s.shape[0]
+    if n > ORDER_MAX:
+        return torch.argsort(s, descending=True, stable=True).to(torch.int32)
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    h = handle(dev)
+    _call(h, "bf_score_order", h.lib.bf_score_order, h.h, ptr(s), n, ptr(order), h.stream())
+    return order
 
 
 def last_refine_launch(device=None) -> dict:

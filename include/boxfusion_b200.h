@@ -103,6 +103,13 @@ int bf_corr2d(bf_handle* h, const float* map_corners /*[G,8,3]*/, const int32_t*
               const float* det_xyxy /*[n_small,4]*/, int n_small,
               double* boxes2d /*[G,4] or NULL*/, int32_t* best /*[n_small]*/, double* best_iou /*[n_small]*/, void* stream);
 
+/* ---- A5  the score order of nms_3d, `order = scores.argsort()[::-1]` (instances.py:52), on the device --------
+ * order[r] = index of the r-th highest score; equal scores keep ascending index (a stable descending sort, what the
+ * Python binding obtains from torch.argsort(descending=True, stable=True); NumPy's own argsort is unstable for exact
+ * ties).  NaN scores sort first, -0 == +0.  One CTA, bitonic network in shared memory: N <= 4096
+ * (BF_ERR_INVALID_ARG beyond; callers with larger maps sort elsewhere). */
+int bf_score_order(bf_handle* h, const float* scores /*[N]*/, int N, int32_t* order /*[N]*/, void* stream);
+
 /* ---- A8  BoxManager.compute_pose_disparity (box_manager.py:168-186), batched ------------------- */
 int bf_pose_disparity(bf_handle* h, const float* poses /*[M,16]*/, const int32_t* ia, const int32_t* ib, int n,
                       float* baseline /*[n]*/, float* angle_deg /*[n]*/, void* stream);

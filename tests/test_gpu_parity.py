@@ -238,6 +238,25 @@ def test_corr2d_matches_port():
         assert abs(float(best_iou[k]) - iou.max()) < 1e-12
 
 
+def test_score_order_matches_stable_descending_argsort():
+    """bf_score_order == torch.argsort(descending=True, stable=True) (the order nms_3d consumes, instances.py:52), incl. exact
+    ties (ascending index), -0/+0, NaN first, every size class of the bitonic network."""
+    rs = np.random.RandomState(4)
+    for n in (1, 2, 3, 31, 32, 33, 250, 1000, 1024, 1025, 4095, 4096):
+        s = rs.uniform(0.0, 1.0, n).astype(np.float32)
+        if n > 8:
+            s[rs.randint(0, n, n // 4)] = s[rs.randint(0, n, n // 4)]          # exact ties
+            s[1], s[5] = 0.0, -0.0
+            s[3] = np.nan
+            s[7] = -1.5
+        t = torch.from_numpy(s).cuda()
+        want = torch.argsort(t, descending=True, stable=True).to(torch.int32)
+        got = ops.score_order(t)
+        assert torch.equal(want, got), n
+    big = torch.rand(5000, device="cuda")                                       # beyond the single-CTA limit: torch path
+    assert torch.equal(ops.score_order(big), torch.argsort(big, descending=True, stable=True).to(torch.int32))
+
+
 # ---- A16-A22 refinement ----------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("V", [3, 5, 8])
