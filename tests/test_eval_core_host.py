@@ -66,6 +66,16 @@ def _gen(kind, rs):
         b[:k] = c + rs.randint(-6, 7, (k, 2)) * 4.0
     elif kind == "sub_pixel":
         c = rs.uniform([50, 50], [W - 50, H - 50]); a = c + rs.normal(0, 0.01, (8, 2)); b = c + rs.normal(0, 0.01, (8, 2))
+    elif kind == "nearly_identical":   # shallow crossings, vertices within the classification margin of the other boundary
+        c = rs.uniform([50, 50], [W - 50, H - 50]); base = rs.normal(0, 40, (3, 2))
+        sg = np.array([[i & 1, (i >> 1) & 1, (i >> 2) & 1] for i in range(8)]) - 0.5
+        eps = 10.0 ** rs.uniform(-4, 0)
+        a = c + sg @ base; b = c + sg @ (base + rs.normal(0, eps, (3, 2))) + rs.normal(0, eps, 2)
+    elif kind == "tiny_rotation":
+        c = rs.uniform([80, 80], [W - 80, H - 80]); base = rs.normal(0, 30, (3, 2))
+        sg = np.array([[i & 1, (i >> 1) & 1, (i >> 2) & 1] for i in range(8)]) - 0.5
+        th = 10.0 ** rs.uniform(-6, -1); R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        a = c + sg @ base; b = c + (sg @ base) @ R.T * (1 + rs.normal(0, 1e-4))
     else:   # "box_like": two projected parallelepipeds, slightly different
         c = rs.uniform([50, 50], [W - 50, H - 50]); base = rs.normal(0, 40, (3, 2))
         sg = np.array([[i & 1, (i >> 1) & 1, (i >> 2) & 1] for i in range(8)]) - 0.5
@@ -75,7 +85,7 @@ def _gen(kind, rs):
 
 @pytest.mark.parametrize("rolled", [0, 1])          # the kernel's two code-size variants of the same evaluation
 @pytest.mark.parametrize("kind", ["generic", "integer_grid", "clamped_to_border", "identical", "shared_vertices",
-                                  "sub_pixel", "box_like"])
+                                  "sub_pixel", "box_like", "nearly_identical", "tiny_rotation"])
 def test_polygon_iou_bit_exact(libs, kind, rolled):
     lh, lo = libs
     rs = np.random.RandomState(abs(hash(kind)) % (2 ** 31))
