@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("BOXFUSION_B200_LIB") or os.path.join(_HERE, "lib", "l
 
 BF_OK, BF_ERR_INVALID_ARG, BF_ERR_CUDA, BF_ERR_CAPACITY = 0, -1, -2, -3
 IOU_SAMPLED_REF, IOU_ANALYTIC = 0, 1
+OPT_REFINE_CONCURRENT = 1
 _ERR = {-1: "BF_ERR_INVALID_ARG", -2: "BF_ERR_CUDA", -3: "BF_ERR_CAPACITY"}
 
 _vp, _i32, _f32, _f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
@@ -76,6 +77,7 @@ PROTOTYPES = {
     "bf_engine_apply": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bf_detection_filter": (_i32, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _f64, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
+    "bf_set_option": (_i32, [_vp, _i32, _i32]),
     "bf_refine_last_launch": (_i32, [_vp]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
 }

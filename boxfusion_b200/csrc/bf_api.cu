@@ -31,6 +31,12 @@ extern "C" int bf_create(int device, bf_handle** out) {
     return BF_OK;
 }
 
+extern "C" int bf_set_option(bf_handle* h, int key, int value) {
+    if (!h) return BF_ERR_INVALID_ARG;
+    if (key == BF_OPT_REFINE_CONCURRENT) { h->refine_concurrent = value ? 1 : 0; return BF_OK; }
+    return bf_fail(h, BF_ERR_INVALID_ARG, "bf_set_option", "unknown key");
+}
+
 extern "C" void bf_destroy(bf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);

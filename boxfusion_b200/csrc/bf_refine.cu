@@ -453,6 +453,11 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
         while (bestC > 1 && (long long)B * bestC > 8LL * h->sm_count) bestC /= 2;
         best_cost = 0.0;
     }
+    if (!saturated && h->refine_concurrent) {                      // BF_OPT_REFINE_CONCURRENT: leave room for the other streams' kernels
+        variant = 1; bestT = 256; bestC = 16;
+        while (bestC > 1 && (long long)(bestC / 2) * bestT >= items_max) bestC /= 2;
+        best_cost = 0.0;
+    }
     if (h->refine_force_c > 0 && h->refine_force_t > 0) {          // BF_REFINE_SHAPE (tuning sweeps)
         variant = (h->refine_force_variant >= 0 && h->refine_force_variant < 3) ? h->refine_force_variant : variant;
         if (h->refine_force_t <= kernel_max_t[variant]) { bestC = h->refine_force_c; bestT = h->refine_force_t; best_cost = 0.0; }

@@ -63,6 +63,7 @@ class FusionEngine:
             raise ValueError("map_capacity is limited to 65536 rows")
         if private_stream:
             self.h = Handle(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+            self.h.check(self.h.lib.bf_set_option(self.h.h, 1, 1), "bf_set_option")     # BF_OPT_REFINE_CONCURRENT
             self.stream = torch.cuda.Stream(self.dev)
         else:
             self.h = handle(self.dev)

@@ -142,6 +142,13 @@ int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,
               float* out_xyzlhw /*[B,6]*/, int32_t* out_updated /*[B]*/, int32_t* out_iters /*[B]*/,
               float* trace /*[B,iters,8] or NULL: success,min_iou,search[6]*/, int32_t* status /*[1]*/, void* stream);
 
+/* Per-handle options.  BF_OPT_REFINE_CONCURRENT = 1: the caller drives several handles concurrently on their own streams
+ * (independent sequences, bench.py --workload c5); small bf_refine calls then use 256-thread CTAs of the 80-register
+ * instantiation, which can share an SM with another stream's kernels, instead of the shape that minimises the latency of
+ * a lone call (+11 % keyframes/s with 8 concurrent sequences per GPU).  Results are identical.  No reference counterpart. */
+enum { BF_OPT_REFINE_CONCURRENT = 1 };
+int bf_set_option(bf_handle* h, int key, int value);
+
 /* Diagnostic: how the last bf_refine call of this handle was launched: kernel instantiation * 1000000 (0 = latency
  * regime, 1 = mid, 2 = saturated / compact code) + cluster size * 1000 + block size.  No reference counterpart. */
 int bf_refine_last_launch(bf_handle* h);
