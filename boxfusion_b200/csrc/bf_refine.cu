@@ -4,9 +4,11 @@
 // optimiser around it (evaluate_iou :413-461, cal_transform :475-535, update_PST :537-562,
 // init_opt_params :566-600, boxfusion loop :651-721).  The reference launches one tiny kernel per
 // optimiser iteration per box with 13 blocking copies each; here ONE launch refines every box: one
-// CTA per map box, all iterations inside the kernel, particles in registers, per-view observation
-// hulls precomputed once in shared memory, the ordered "first 200 better particles" rule done with
-// a ballot/popc prefix selection and the float32 sums accumulated in the reference's index order.
+// thread-block cluster per map box, all iterations inside the kernel, one (view, particle) evaluation per
+// work item (bf_refine_eval.cuh), per-view observation hulls and edge lines precomputed once in shared
+// memory, contributions gathered in the cluster leader's shared memory through DSMEM, the ordered
+// "first 200 better particles" rule done as one block-wide ballot/prefix scan and the float32 sums
+// accumulated in the reference's index order.
 //
 // THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: every float expression below is evaluated
 // with the same IEEE operations, in the same order, as the reference kernel compiled without

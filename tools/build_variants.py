@@ -1,7 +1,10 @@
 """Kernel-tuning builds: compile bf_refine.cu with extra -D flags into boxfusion_b200/lib/variants/lib_<name>.so
 (the other objects are shared with the production build).  Select one at run time with BOXFUSION_B200_LIB=<path>.
 
-    python tools/build_variants.py name1="-DBF_OPT_ROLL_S -DBF_OPT_ROLL_T" name2="..."
+    python tools/build_variants.py base="" slots256="-DBF_CNT_SLOTS=256" ...   # name=extra nvcc flags (any -D the sources honour)
+
+The round-1 sweep (profiles/r1_v10_variant_shape_sweep.txt) used this with the then compile-time switches for rolled loops and
+register caps; the winners became the three template instantiations of bf_refine_kernel.
 """
 import os
 import subprocess

@@ -1,5 +1,6 @@
 #!/bin/bash
-# tuning sweep: kernel variant x forced launch shape, C4 / C1 kernel-level cases
+# tuning sweep: build variant (tools/build_variants.py name=flags ...) x forced launch shape (BF_REFINE_SHAPE), C1 / C4 kernel-level cases
+# usage: bash tools/sweep_shapes.sh name1 name2 ...   (names of lib_<name>.so under boxfusion_b200/lib/variants)
 for v in "$@"; do
   for shape in auto 1,256 2,256 4,256 8,256 2,128 4,128 8,128; do
     if [ "$shape" = auto ]; then unset BF_REFINE_SHAPE; else export BF_REFINE_SHAPE=$shape; fi
