@@ -55,8 +55,6 @@ class FusionEngine:
         """private_stream=True gives the engine its own CUDA stream and its own library handle (scratch), so that
         several engines - independent sequences - can be driven concurrently from one host thread with
         step_launch() / step_finish() (bench.py --workload c5)."""
-        if cfg["box_fusion"].get("check_valid"):
-            raise NotImplementedError("check_valid (box_manager.py:151-166) is not part of the device-resident engine")
         self.cfg = cfg
         self.dev = ops._dev(device if str(device) != "cuda" else None)
         if map_capacity > 65536:
@@ -114,6 +112,7 @@ class FusionEngine:
         for m in self._maps:
             m["_p"] = {k: m[k].data_ptr() for k, _, _ in _MAP_FIELDS}
         self._order = torch.zeros(self.ncap, dtype=torch.int32, device=d)
+        self._arange = torch.arange(self.ncap, dtype=torch.int32, device=d)
         self._p["order"] = self._order.data_ptr()
         self._stream_ptr = self.stream.cuda_stream if self.stream is not None else None
         if self.stream is not None:
@@ -226,6 +225,18 @@ class FusionEngine:
              ctypes.byref(other["_c"]), P["info"], st)
         self._cur = 1 - self._cur
         mp = self.map
+        if bf.get("check_valid"):
+            # BoxManager.check_valid_num (box_manager.py:151-166, demo.py:297-298; only when a new box survived, demo.py:269):
+            # drop map rows never re-observed (valid_num == 0) that are older than `gap` keyframes - one more compaction.
+            # The row count of the compacted map is still on the device (info[1]), so the flags are formed there.
+            thr = self.count - int(self.cfg["data"]["gap"])
+            stale = (mp["valid"][:Nall] == 0) & (mp["frame_id"][:Nall] < thr) & (self.info[0] != 0)
+            self.keep[:Nall].copy_(((self._arange[:Nall] < self.info[1]) & ~stale).to(torch.int32))
+            other = self._maps[1 - self._cur]
+            call("bf_engine_compact", lib.bf_engine_compact, h.h, P["keep"], Nall, ctypes.byref(mp["_c"]),
+                 ctypes.byref(other["_c"]), P["info"], st)
+            self._cur = 1 - self._cur
+            mp = self.map
         # STEP 3: multi-view box fusion (demo.py:304-305): selection now, refinement after the read-back
         if bf["use"]:
             call("bf_engine_select", lib.bf_engine_select, h.h, ctypes.byref(mp["_c"]), ctypes.byref(self._fused_c),

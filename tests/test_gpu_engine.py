@@ -71,6 +71,36 @@ def test_engine_matches_api_longer_sequence():
     assert torch.equal(per.projected_boxes.cpu(), sess.per_frame_ins.projected_boxes.cpu())
 
 
+def test_check_valid_num_three_way():
+    """cfg box_fusion.check_valid = True (BoxManager.check_valid_num, box_manager.py:151-166; off in the shipped configs):
+    map boxes never re-observed are dropped after `gap` keyframes.  CPU port == reference-shaped CUDA API == engine."""
+    from oracle import port
+    port.IOU_BACKEND = "c"
+    scene = SyntheticScene(n_objects=60, seed=21, max_det=20, shape="scannet", new_frac=0.35)
+    cfg = make_cfg("scannet", pst_path=make_pst(256, seed=0), pst_size=256)
+    cfg["box_fusion"]["check_valid"] = True
+    cfg["data"]["gap"] = 2
+    eng = FusionEngine(cfg, map_capacity=1024, store_capacity=4096)
+    sess, ref = FusionSession(api, cfg, device="cuda"), FusionSession(port, cfg)
+    dropped = 0
+    for k in range(24):
+        kf = scene.keyframe(k)
+        eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+        ins_b, pose_np = ref.make_pred_instances(kf)
+        ins_a, _ = sess.pred_instances_from_world(kf, ins_b.pred_boxes_3d.tensor.numpy(), ins_b.pred_boxes_3d.R.numpy(),
+                                                  ins_b.projected_boxes.numpy())
+        before = len(sess.all_pred_box) if sess.all_pred_box is not None else 0
+        sess.step(kf, ins_a, pose_np)
+        ref.step(kf, ins_b, pose_np)
+        a, b, c = eng.snapshot(), sess.snapshot(), ref.snapshot()
+        for key in KEYS:
+            assert b[key].shape == c[key].shape and np.array_equal(_bits(b[key]), _bits(c[key])), ("api vs port", k, key)
+            assert a[key].shape == b[key].shape and np.array_equal(_bits(a[key]), _bits(b[key])), ("engine vs api", k, key)
+        if sess.last_keep_idx is not None:
+            dropped += max(0, len(sess.last_keep_idx) - len(sess.all_pred_box))
+    assert dropped > 0, "the scene must exercise check_valid_num"
+
+
 def test_engine_empty_keyframe_and_capacity():
     scene = SyntheticScene(n_objects=20, seed=2, max_det=8)
     cfg = make_cfg("ca1m", pst_path=make_pst(64), pst_size=64)

@@ -164,3 +164,26 @@ def test_live_reference_vs_port_sequence(monkeypatch):
         sa, sb = a.snapshot(), b.snapshot()
         for key in sa:
             assert sa[key].shape == sb[key].shape and np.array_equal(_bits(sa[key]), _bits(sb[key])), (k, key)
+
+
+@needs_ref
+def test_live_reference_vs_port_check_valid(monkeypatch):
+    """BoxManager.check_valid_num (box_manager.py:151-166, cfg box_fusion.check_valid; off in the shipped configs): the
+    unmodified reference against the port on a scene where boxes are never re-observed and get dropped."""
+    monkeypatch.setattr(port, "IOU_BACKEND", "c")
+    ref = rh.load_reference()
+    scene = SyntheticScene(n_objects=40, seed=21, max_det=12, shape="scannet", new_frac=0.35)
+    cfg = make_cfg("scannet", pst_path=os.path.join(rh.REFERENCE_ROOT, "data", "pst_1024_0.tiff"), pst_size=1024)
+    cfg["box_fusion"]["check_valid"] = True
+    cfg["data"]["gap"] = 2
+    a, b = FusionSession(ref, cfg), FusionSession(port, cfg)
+    dropped = 0
+    for k in range(8):
+        kf = scene.keyframe(k)
+        a.step(kf); b.step(kf)
+        sa, sb = a.snapshot(), b.snapshot()
+        for key in sa:
+            assert sa[key].shape == sb[key].shape and np.array_equal(_bits(sa[key]), _bits(sb[key])), (k, key)
+        if a.last_keep_idx is not None:
+            dropped += max(0, len(a.last_keep_idx) - len(a.all_pred_box))
+    assert dropped > 0
