@@ -65,6 +65,7 @@ PROTOTYPES = {
     "bf_nms3d": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f32, _f32, _f32, _i32,
                         _vp, _vp, _vp, _vp]),
     "bf_corr2d": (_i32, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "bf_points_in_hull": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bf_score_order": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bf_pose_disparity": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bf_refine": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, ctypes.POINTER(RefineCfg),

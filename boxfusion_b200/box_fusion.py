@@ -139,6 +139,15 @@ class BoxFusion(object):
         mean[3:6] = np.mean(np.sort(box_3d[:, 3:], axis=1)[:, list(rank)], axis=0)
         return mean, per_boxes_3d_R[best]
 
+    def init_opt_params_v2(self, box_3d, per_boxes_3d_R, per_boxes_3d_scores, verbose=False):
+        """box_fusion.py:602-619 (plain means; unused by the reference's own boxfusion loop)."""
+        box_3d = np.asarray(box_3d)
+        best = int(np.argmax(per_boxes_3d_scores))
+        mean = np.zeros(6)
+        mean[:3] = np.mean(box_3d[:, :3], axis=0)
+        mean[3:6] = np.mean(box_3d[:, 3:], axis=0)
+        return mean, per_boxes_3d_R[best]
+
     # ---- the hot path (box_fusion.py:622-724) --------------------------------------------------------
     def boxfusion(self, all_pred_box, per_frame_box, box_manager, beta=0.9, verbose=False):
         N_box = len(all_pred_box)

@@ -329,3 +329,27 @@ extern "C" int bf_iou3d_matrix(bf_handle* h, const float* cornersA, int M, const
     }
     return BF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Instances3D.batch_in_convex_hull_3d (instances.py:559-571): points against the 12 hull planes of one box.
+__global__ void bf_points_in_hull_kernel(const float* __restrict__ corners, const double* __restrict__ points, int n,
+                                         uint8_t* __restrict__ inside) {
+    __shared__ double pl[48];
+    if (threadIdx.x < 6) {
+        float c[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) c[k] = corners[k];
+        bf_face_planes(c, threadIdx.x, pl + 8 * threadIdx.x);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inside[i] = bf_inside12(pl, points[3 * (size_t)i], points[3 * (size_t)i + 1], points[3 * (size_t)i + 2]) ? 1 : 0;
+}
+
+extern "C" int bf_points_in_hull(bf_handle* h, const float* corners, const double* points, int n, uint8_t* inside, void* stream) {
+    if (!h || n < 0 || (n > 0 && (!corners || !points || !inside))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_points_in_hull", "bad argument");
+    if (n == 0) return BF_OK;
+    bf_points_in_hull_kernel<<<bf_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(corners, points, n, inside);
+    BF_LAUNCH_CHECK(h, "bf_points_in_hull_kernel");
+    return BF_OK;
+}

@@ -322,6 +322,47 @@ class Instances3D:
         return float(ops.iou3d_matrix(a, b, IOU_MODE)[0, 0].item())
 
     @staticmethod
+    def augment_vertices(corners):
+        """8 corners + the 12 edge mid-points, in the reference's edge order (instances.py:493-512) -> [20,3]."""
+        c = np.asarray(corners)
+        edges = ((0, 1), (0, 4), (1, 5), (4, 5), (2, 3), (2, 6), (6, 7), (3, 7), (0, 3), (4, 7), (1, 2), (5, 6))
+        return np.vstack([c, [(c[a] + c[b]) / 2 for a, b in edges]])
+
+    @staticmethod
+    def batch_in_convex_hull_3d(points, corners):
+        """Which points satisfy every hull half-space of the box within 1e-6 (instances.py:559-571) -> bool [n] (numpy)."""
+        return ops.points_in_hull(points, corners).cpu().numpy()
+
+    @staticmethod
+    def check_intersection(corners1, corners2):
+        """The containment gate of obb_iou (instances.py:514-557): any of the 20 augmented points of one box inside the other."""
+        a1, a2 = Instances3D.augment_vertices(corners1), Instances3D.augment_vertices(corners2)
+        return bool(ops.points_in_hull(a1, corners2).any().item() or ops.points_in_hull(a2, corners1).any().item())
+
+    @staticmethod
+    def IoU_2D(A, B):
+        """AABB of the point set A against boxes B (instances.py:616-641) -> (iou, overlap_A), float64; unused by the
+        reference's own pipeline, trivial host arithmetic kept for API completeness."""
+        A = np.asarray(A).astype(np.float64)
+        B = np.asarray(B)
+        x0, y0 = np.min(A, axis=0)
+        x1, y1 = np.max(A, axis=0)
+        area_a = (x1 - x0) * (y1 - y0)
+        area_b = (B[:, 2] - B[:, 0]) * (B[:, 3] - B[:, 1])
+        iw = np.maximum(0, np.minimum(x1, B[:, 2]) - np.maximum(x0, B[:, 0]))
+        ih = np.maximum(0, np.minimum(y1, B[:, 3]) - np.maximum(y0, B[:, 1]))
+        inter = iw * ih
+        return inter / (area_a + area_b - inter + 1e-6), inter / (area_a + 1e-6)
+
+    @staticmethod
+    def modify_instance(ind_old, ind_new, old_ins, new_ins):
+        """Overwrite one instance with another's fields in place (instances.py:400-408; unused by demo.py)."""
+        for f in ("scores", "pred_classes", "pred_boxes", "pred_logits", "object_desc", "pred_proj_xy"):
+            old_ins.get(f)[ind_old] = new_ins.get(f)[ind_new]
+        old_ins.pred_boxes_3d.tensor[ind_old] = new_ins.pred_boxes_3d.tensor[ind_new]
+        old_ins.pred_boxes_3d.R[ind_old] = new_ins.pred_boxes_3d.R[ind_new]
+
+    @staticmethod
     def project_3d_to_2d_box(boxes_3d, K, pose, H, W, frame_id=None):
         """Clipped 2-D AABB of map boxes in the current view (instances.py:670-717) -> float64 [N,4] (numpy)."""
         b = np.asarray(boxes_3d, dtype=np.float32).reshape(-1, 8, 3)

@@ -22,7 +22,7 @@ MAX_VIEWS = 64
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
                     "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1,
                     "bf_engine_ingest": 1, "bf_engine_corr": 1, "bf_engine_compact": 2, "bf_engine_select": 1,
-                    "bf_engine_apply": 1, "bf_detection_filter": 1, "bf_score_order": 1}
+                    "bf_engine_apply": 1, "bf_detection_filter": 1, "bf_score_order": 1, "bf_points_in_hull": 1}
 
 
 class Profile:
@@ -236,6 +236,17 @@ def refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, 
                             ptr(off), ptr(idx), B, ctypes.byref(rcfg), ptr(out), ptr(upd), ptr(its), ptr(trace),
                             ptr(status), h.stream())
     return out, upd, its, trace, status
+
+
+def points_in_hull(points, corners) -> torch.Tensor:
+    """Instances3D.batch_in_convex_hull_3d (instances.py:559-571): bool [n], points against the hull of 8 corners."""
+    dev = _pick_device(points, corners)
+    c = dev_tensor(np.asarray(corners, dtype=np.float32) if not isinstance(corners, torch.Tensor) else corners, torch.float32, dev).reshape(8, 3)
+    p = dev_tensor(np.asarray(points, dtype=np.float64) if not isinstance(points, torch.Tensor) else points, torch.float64, dev).reshape(-1, 3)
+    out = torch.empty(p.shape[0], dtype=torch.uint8, device=dev)
+    h = handle(dev)
+    _call(h, "bf_points_in_hull", h.lib.bf_points_in_hull, h.h, ptr(c), ptr(p), p.shape[0], ptr(out), h.stream())
+    return out.to(torch.bool)
 
 
 ORDER_MAX = 4096

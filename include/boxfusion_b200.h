@@ -103,6 +103,13 @@ int bf_corr2d(bf_handle* h, const float* map_corners /*[G,8,3]*/, const int32_t*
               const float* det_xyxy /*[n_small,4]*/, int n_small,
               double* boxes2d /*[G,4] or NULL*/, int32_t* best /*[n_small]*/, double* best_iou /*[n_small]*/, void* stream);
 
+/* ---- A3  Instances3D.batch_in_convex_hull_3d (instances.py:559-571) -------------------------------------------
+ * inside[i] = 1 when point i satisfies n.p + d <= 1e-6 for the 12 hull half-spaces of the box (the same planes and
+ * predicate bf_iou3d_matrix uses for the containment gate and the 25^3 counts).  Helper entry for the drop-in's
+ * check_intersection / batch_in_convex_hull_3d; the association path itself never calls it. */
+int bf_points_in_hull(bf_handle* h, const float* corners /*[8,3]*/, const double* points /*[n,3]*/, int n,
+                      uint8_t* inside /*[n]*/, void* stream);
+
 /* ---- A5  the score order of nms_3d, `order = scores.argsort()[::-1]` (instances.py:52), on the device --------
  * order[r] = index of the r-th highest score; equal scores keep ascending index (a stable descending sort, what the
  * Python binding obtains from torch.argsort(descending=True, stable=True); NumPy's own argsort is unstable for exact

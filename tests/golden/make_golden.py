@@ -130,13 +130,47 @@ def gen_refine(ref, pst):
     np.savez_compressed(os.path.join(HERE, "refine_cases.npz"), **out)
 
 
+def gen_hull_helpers(ref):
+    """The small public helpers around obb_iou (instances.py:493-571, 616-641) and init_opt_params_v2
+    (box_fusion.py:602-619), run on the pairs of iou_pairs.npz: `python tests/golden/make_golden.py helpers` adds this
+    fixture without touching the others."""
+    g = np.load(os.path.join(HERE, "iou_pairs.npz"))
+    corners = g["corners"]
+    rs = np.random.RandomState(5)
+    sel = rs.choice(len(g["ia"]), 600, replace=False)
+    pa = np.concatenate([corners[g["ia"][sel]], g["ov_a"]]).astype(np.float32)
+    pb = np.concatenate([corners[g["ib"][sel]], g["ov_b"]]).astype(np.float32)
+    gate = np.array([ref.Instances3D.check_intersection(a, b) for a, b in zip(pa, pb)])
+    pts, inside = [], []
+    for a, b in zip(g["ov_a"][:80], g["ov_b"][:80]):
+        lo, hi = np.minimum(a.min(0), b.min(0)), np.maximum(a.max(0), b.max(0))
+        p = np.concatenate([rs.uniform(lo, hi, (40, 3)), ref.Instances3D.augment_vertices(a.astype(np.float32)).astype(np.float64),
+                            a.astype(np.float64)])          # random points, the partner's 20 gate points, own corners (on the hull)
+        pts.append(p); inside.append(ref.Instances3D.batch_in_convex_hull_3d(p, b))
+    aug = np.stack([ref.Instances3D.augment_vertices(c) for c in corners[:6]])
+    A2 = rs.uniform(0, 300, (20, 8, 2)).astype(np.float32)
+    B2 = np.sort(rs.uniform(0, 300, (20, 7, 2, 2)), axis=2).reshape(20, 7, 4)[..., [0, 2, 1, 3]]
+    i2 = np.stack([np.stack(ref.Instances3D.IoU_2D(a, b)) for a, b in zip(A2, B2)])
+    bf = ref.BoxFusion(make_cfg("ca1m", pst_path=REF_PST, pst_size=1024))
+    vb = rs.uniform(0.2, 2.0, (9, 5, 6)); vs = rs.uniform(0, 1, (9, 5)); vR = rs.normal(0, 1, (9, 5, 3, 3))
+    v2 = [bf.init_opt_params_v2(b, r, s_) for b, r, s_ in zip(vb, vR, vs)]
+    np.savez_compressed(os.path.join(HERE, "hull_helpers.npz"), pa=pa, pb=pb, gate=gate, pts=np.stack(pts), pts_box=g["ov_b"][:80],
+                        inside=np.stack(inside), aug_in=corners[:6], aug=aug, iou2d_A=A2, iou2d_B=B2, iou2d=i2,
+                        v2_boxes=vb, v2_scores=vs, v2_R=vR, v2_mean=np.stack([m for m, _ in v2]), v2_rot=np.stack([r for _, r in v2]))
+    print("hull_helpers: gate true for", int(gate.sum()), "of", len(gate), "pairs; inside", int(np.stack(inside).sum()), "of", np.stack(inside).size)
+
+
 def main():
     ref = rh.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "helpers":
+        gen_hull_helpers(ref)
+        return
     pst = gen_pst(ref)
     for name, spec in SEQUENCES.items():
         gen_sequence(ref, name, spec)
     gen_iou_pairs(ref)
     gen_refine(ref, pst)
+    gen_hull_helpers(ref)
     import scipy
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "torch": torch.__version__,
             "reference": "pliam1105/BoxFusion @ /root/reference", "sequences": SEQUENCES,

@@ -238,6 +238,18 @@ def test_corr2d_matches_port():
         assert abs(float(best_iou[k]) - iou.max()) < 1e-12
 
 
+def test_hull_helpers_match_reference_golden(golden_dir):
+    """Instances3D.check_intersection / batch_in_convex_hull_3d (instances.py:514-571) through bf_points_in_hull against the
+    unmodified reference's answers on 840 box pairs (251 passing the gate) and 5 440 points (random, gate points, points on
+    the hull itself)."""
+    g = np.load(os.path.join(golden_dir, "hull_helpers.npz"))
+    for a, b, want in zip(g["pa"], g["pb"], g["gate"]):
+        assert api.Instances3D.check_intersection(a, b) == bool(want)
+    for p, box, want in zip(g["pts"], g["pts_box"], g["inside"]):
+        got = api.Instances3D.batch_in_convex_hull_3d(p, box)
+        assert got.dtype == np.bool_ and np.array_equal(got, want)
+
+
 def test_score_order_matches_stable_descending_argsort():
     """bf_score_order == torch.argsort(descending=True, stable=True) (the order nms_3d consumes, instances.py:52), incl. exact
     ties (ascending index), -0/+0, NaN first, every size class of the bitonic network."""

@@ -129,3 +129,24 @@ def test_post_process_filter():
     ext = c.max(1) - c.min(1)
     assert np.array_equal(results.post_process(c, 0.3), c[(ext >= 0.3).all(1)])
     assert torch.equal(results.post_process(torch.from_numpy(c), 0.3), torch.from_numpy(c[(ext >= 0.3).all(1)]))
+
+
+def test_small_public_helpers_match_reference_golden(golden_dir):
+    """augment_vertices / IoU_2D / init_opt_params_v2 (instances.py:493-512, 616-641; box_fusion.py:602-619): host
+    arithmetic mirrors kept for API completeness, against values produced by the unmodified reference
+    (tests/golden/make_golden.py helpers)."""
+    import os
+    import numpy as np
+    from boxfusion_b200 import api
+    from boxfusion_b200.synthetic import make_cfg, make_pst
+    g = np.load(os.path.join(golden_dir, "hull_helpers.npz"))
+    for c, want in zip(g["aug_in"], g["aug"]):
+        got = api.Instances3D.augment_vertices(c)
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+    for A, B, want in zip(g["iou2d_A"], g["iou2d_B"], g["iou2d"]):
+        iou, ov = api.Instances3D.IoU_2D(A, B)
+        assert np.array_equal(iou, want[0]) and np.array_equal(ov, want[1])
+    bf = api.BoxFusion(make_cfg("ca1m", pst_path=make_pst(64, seed=0), pst_size=64))
+    for b, r, s_, m, rot in zip(g["v2_boxes"], g["v2_R"], g["v2_scores"], g["v2_mean"], g["v2_rot"]):
+        mean, R = bf.init_opt_params_v2(b, r, s_)
+        assert np.array_equal(mean, m) and np.array_equal(R, rot)
