@@ -368,6 +368,95 @@ def run_c5(args, rank, world, local_rank):
                       "gpu_launches": int(ops.Profile.launches), "wall_s": round(t, 3)}))
 
 
+def _time_sharded(fn, world, dev, steps, warmup):
+    """W warm-up + K timed repetitions of one sharded step, CUDA events, L2 flushed between repetitions, max over ranks."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(warmup, 3)):
+        fn()
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    t = torch.tensor([float(np.median(ms))], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_c4(args, rank, world, local_rank):
+    """BASELINE configs[3]: 4096 particles x 32 views x 128 boxes, 20 forced iterations, the boxes of the one call sharded
+    over the ranks (boxfusion_b200/sharding.py::refine_sharded, SURVEY 8(e) axis 2) + all_gather of the fused rows."""
+    from boxfusion_b200 import ops
+    from boxfusion_b200.sharding import refine_sharded
+    from boxfusion_b200.synthetic import make_pst, refine_problem
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, V, P = 128, 32, 4096
+    prob = refine_problem(B, V, seed=11)
+    Wi, Hi = prob["size"]
+    pst = torch.from_numpy(make_pst(P, seed=1)).to(dev)
+    cfg = make_cfg("ca1m", pst_path=None, pst_size=P)
+    K16 = np.eye(4, dtype=np.float32); K16[:3, :3] = prob["K"]
+    t = torch.from_numpy(prob["tensor"].reshape(-1, 6)).to(dev); R = torch.from_numpy(prob["R"].reshape(-1, 9)).to(dev)
+    s = torch.from_numpy(prob["scores"].reshape(-1)).to(dev); po = torch.from_numpy(prob["poses"].reshape(-1, 16)).to(dev)
+    uv = ops.project_boxes(ops.box_corners(t, R), torch.linalg.inv(po.reshape(-1, 4, 4)), prob["K"], Wi, Hi).reshape(-1, 16)
+    off = np.arange(B + 1, dtype=np.int32) * V
+    idx = torch.arange(B * V, dtype=torch.int32, device=dev)
+    rcfg = ops.make_refine_cfg(cfg, K16.reshape(-1), Hi, Wi, early_stop=False)
+    res = {}
+    if world > 1:
+        fn = lambda: res.__setitem__("o", refine_sharded(pst, t, R, s, uv, po, off, idx, rcfg))       # noqa: E731
+    else:
+        fn = lambda: res.__setitem__("o", ops.refine(pst, t, R, s, uv, po, off, idx, rcfg, max_views=V)[:3])   # noqa: E731
+    ms = _time_sharded(fn, world, dev, min(args.steps, 10), args.warmup)
+    out, upd, its = res["o"]
+    assert out.shape[0] == B and int(its.min()) == 20
+    if rank != 0:
+        return
+    evals = float(B) * V * P * 20
+    print(json.dumps({"metric": "particle-view evaluations/s, BASELINE configs[3] (4096 x 32 x 128, 20 forced iterations), boxes sharded over the GPUs",
+                      "value": round(evals / (ms * 1e-3), 1), "unit": "evals/s", "n_gpus": world, "steps": min(args.steps, 10), "warmup": max(args.warmup, 3),
+                      "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": {"workload": "C4 particle sweep, one bf_refine call per rank on its block of boxes + all_gather of [B,6] rows",
+                                                      "l2": "flushed between repetitions"},
+                      "checksum_updated_boxes": int(upd.sum().item())}))
+
+
+def run_c3(args, rank, world, local_rank):
+    """BASELINE configs[2]: the 256 x 4096 oriented-3D IoU matrix, rows sharded over the ranks (iou3d_matrix_sharded,
+    SURVEY 8(e) axis 3) + all_gather of the float64 blocks."""
+    from boxfusion_b200 import ops
+    from boxfusion_b200.sharding import iou3d_matrix_sharded
+    from boxfusion_b200.synthetic import map_and_detections
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    (mt, mR, _), (dt, dR, _) = map_and_detections(4096, 256, seed=3, tilt_noise=0.0)
+    ca, cb = ops.box_corners(torch.from_numpy(dt).to(dev), torch.from_numpy(dR).to(dev)), ops.box_corners(torch.from_numpy(mt).to(dev), torch.from_numpy(mR).to(dev))
+    res = {}
+    if world > 1:
+        fn = lambda: res.__setitem__("o", iou3d_matrix_sharded(ca, cb, ops.IOU_SAMPLED_REF))          # noqa: E731
+    else:
+        fn = lambda: res.__setitem__("o", ops.iou3d_matrix(ca, cb, ops.IOU_SAMPLED_REF))              # noqa: E731
+    ms = _time_sharded(fn, world, dev, min(args.steps, 50), args.warmup)
+    iou = res["o"]
+    assert tuple(iou.shape) == (256, 4096)
+    if rank != 0:
+        return
+    print(json.dumps({"metric": "oriented-3D-IoU pairs/s, BASELINE configs[2] (256 x 4096, SAMPLED_REF), rows sharded over the GPUs",
+                      "value": round(256 * 4096 / (ms * 1e-3), 1), "unit": "pairs/s", "n_gpus": world, "steps": min(args.steps, 50),
+                      "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "C3 IoU matrix, one bf_iou3d_matrix call per rank on its row block + all_gather of the [M,N] float64 blocks",
+                                 "l2": "flushed between repetitions"},
+                      "checksum_iou_sum": round(float(iou.sum().item()), 6)}))
+
+
 def cpu_port_run(frames, budget_s, backend="scipy"):
     """Reference algorithm on the host (oracle/port.py): frames processed within `budget_s`."""
     from oracle import port, refine_oracle
@@ -392,7 +481,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=20.0)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = the bench line; c5 = 64 sharded sequences")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c4", "c3"],
+                    help="c2 = the bench line; c5 = 64 sharded sequences; c4 / c3 = one large step sharded inside (boxes / IoU rows)")
     ap.add_argument("--sequences", type=int, default=64)
     ap.add_argument("--concurrent", type=int, default=8, help="c5: sequences driven concurrently per GPU (streams)")
     args = ap.parse_args()
@@ -424,8 +514,8 @@ def main():
 
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.workload == "c5":
-        run_c5(args, rank, world, local_rank)
+    if args.workload in ("c5", "c4", "c3"):
+        {"c5": run_c5, "c4": run_c4, "c3": run_c3}[args.workload](args, rank, world, local_rank)
         if world > 1:
             torch.distributed.destroy_process_group()
         return

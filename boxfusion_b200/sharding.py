@@ -32,3 +32,72 @@ def gather_maps(rows: torch.Tensor, group=None) -> List[torch.Tensor]:
     out = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return [o[: int(s.item())] for o, s in zip(out, sizes)]
+
+
+# ---- sharding inside one step (SURVEY.md section 8(e) axes 2 and 3) ----------------------------------------------------
+# Map boxes of one refinement call are independent, and so are the rows of an IoU matrix: rank r takes a contiguous block,
+# computes it with the single-device library, and one all_gather of the (small) results closes the step.  No collective
+# inside the kernels - there is no exchange step in the algorithm.
+
+def block_range(n: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of n items owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_blocks(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """all_gather of the ranks' contiguous blocks (block_range order) -> the full [n_total, ...] tensor on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nmax = max(block_range(n_total, r, world)[1] - block_range(n_total, r, world)[0] for r in range(world))
+    pad = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    sizes = [block_range(n_total, r, world)[1] - block_range(n_total, r, world)[0] for r in range(world)]
+    assert sizes[rank] == local.shape[0]
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def refine_sharded(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, view_offsets, view_index, rcfg,
+                   refine_fn=None, group=None):
+    """BoxFusion.boxfusion's optimiser (box_fusion.py:651-721) for B boxes, box-sharded over the ranks: every rank holds the
+    whole observation store, refines its block of the CSR with `refine_fn` (default: ops.refine, one bf_refine launch) and
+    all_gathers (out_xyzlhw [B,6], updated [B], iters [B])."""
+    import numpy as np
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    off_h = view_offsets.cpu().numpy() if isinstance(view_offsets, torch.Tensor) else np.asarray(view_offsets)
+    B = len(off_h) - 1
+    lo, hi = block_range(B, rank, world)
+    off = (off_h[lo:hi + 1] - off_h[lo]).astype(np.int32)
+    idx = view_index[int(off_h[lo]):int(off_h[hi])]
+    if hi > lo:
+        if refine_fn is None:
+            from . import ops
+            out, upd, its, _, status = ops.refine(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, off, idx, rcfg,
+                                                  max_views=int(np.max(np.diff(off))))
+            if int(status.item()) != 0:
+                raise RuntimeError("bf_refine: capacity exceeded (views per box or polygon candidates)")
+        else:
+            out, upd, its = refine_fn(pst, per_xyzlhw, per_R, per_scores, per_uv, per_poses, off, idx, rcfg)
+    else:
+        dev = pst.device if isinstance(pst, torch.Tensor) else "cpu"
+        out, upd, its = (torch.zeros((0, 6), dtype=torch.float32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev),
+                         torch.zeros(0, dtype=torch.int32, device=dev))
+    return gather_blocks(out, B, group), gather_blocks(upd, B, group), gather_blocks(its, B, group)
+
+
+def iou3d_matrix_sharded(cornersA: torch.Tensor, cornersB: torch.Tensor, mode: int = 0, iou_fn=None, group=None) -> torch.Tensor:
+    """calculate_obb_iou over all pairs (instances.py:106-125), row-block sharded: rank r computes its rows of the [M,N]
+    float64 matrix with `iou_fn` (default: ops.iou3d_matrix) and the blocks are all_gathered."""
+    if iou_fn is None:
+        from . import ops
+        iou_fn = ops.iou3d_matrix
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    M = cornersA.shape[0]
+    lo, hi = block_range(M, rank, world)
+    if hi > lo:
+        local = iou_fn(cornersA[lo:hi], cornersB, mode)
+    else:
+        local = torch.zeros((0, cornersB.shape[0]), dtype=torch.float64, device=cornersB.device)
+    return gather_blocks(local, M, group)

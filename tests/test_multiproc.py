@@ -55,3 +55,86 @@ def test_two_rank_sharding_and_gather(tmp_path):
     exp = torch.cat([_run_sequence(100 + s) for s in (0, 2, 1, 3)], dim=0).numpy()
     assert got.shape == exp.shape and np.array_equal(got, exp)
     assert sizes.sum() == exp.shape[0] and len(sizes) == 2
+
+
+# ---- sharding inside one step: box-sharded refinement and row-block IoU matrix (SURVEY 8(e) axes 2, 3) ------------------
+def _refine_inputs():
+    from boxfusion_b200.synthetic import make_cfg, make_pst, refine_problem
+    from oracle import port, refine_oracle as ro
+    B, V, P = 5, 3, 64
+    prob = refine_problem(B, V, seed=4)
+    W, H = prob["size"]
+    cfg = make_cfg("ca1m", pst_path=None, pst_size=P)
+    cfg["box_fusion"]["iters"] = 4
+    uv = []
+    for b in range(B):
+        ins = port.Instances3D((H, W))
+        ins.pred_boxes_3d = port.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][b]), torch.from_numpy(prob["R"][b]))
+        ins.cam_pose = torch.from_numpy(prob["poses"][b])
+        ins.project_3d_boxes(prob["K"], H=H, W=W)
+        uv.append(ins.projected_boxes.numpy().reshape(V, 16))
+    cs = ro.make_cfg_struct(cfg, H, W)
+    return prob, np.stack(uv), make_pst(P, seed=1), ro.K16_from_K3(prob["K"]), cs, B, V
+
+
+def _oracle_refine_fn(K16, cs):
+    """ops.refine's contract (CSR in, (out, updated, iters) out) served by the CPU oracle: what is under test is the
+    partitioning and the gathers of sharding.refine_sharded, not the arithmetic."""
+    from oracle import refine_oracle as ro
+
+    def fn(pst, t, R, s, uv, po, off, idx, rcfg):
+        out, upd, its = [], [], []
+        for b in range(len(off) - 1):
+            v = np.asarray(idx[off[b]:off[b + 1]])
+            u, o6, n_it, _ = ro.refine_box(t[v], R[v], s[v], uv[v], po[v], pst, K16, cs)
+            out.append(o6 if u else np.zeros(6, np.float32)); upd.append(int(u)); its.append(n_it)
+        return (torch.from_numpy(np.asarray(out, np.float32).reshape(-1, 6)), torch.tensor(upd, dtype=torch.int32),
+                torch.tensor(its, dtype=torch.int32))
+    return fn
+
+
+def _worker_step(rank, world, port_no, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from boxfusion_b200.sharding import iou3d_matrix_sharded, refine_sharded
+    from oracle import port
+    prob, uv, pst, K16, cs, B, V = _refine_inputs()
+    off = np.arange(B + 1, dtype=np.int32) * V
+    idx = np.arange(B * V, dtype=np.int32)
+    out, upd, its = refine_sharded(pst, prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 3, 3), prob["scores"].reshape(-1),
+                                   uv.reshape(-1, 16), prob["poses"].reshape(-1, 4, 4), off, idx, None,
+                                   refine_fn=_oracle_refine_fn(K16, cs))
+    ca = port.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][:, 0]), torch.from_numpy(prob["R"][:, 0])).corners
+    cb = port.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][:, 1]), torch.from_numpy(prob["R"][:, 1])).corners
+    port.IOU_BACKEND = "c"
+    iou = iou3d_matrix_sharded(ca, cb, 0, iou_fn=lambda a, b, mode: torch.from_numpy(
+        np.stack([port.calculate_obb_iou(x.numpy(), b.numpy()) for x in a]).reshape(a.shape[0], b.shape[0])))
+    if rank == 1:                     # every rank holds the full result: check the non-zero rank's copy
+        np.savez(os.path.join(out_dir, "step.npz"), out=out.numpy(), upd=upd.numpy(), its=its.numpy(), iou=iou.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_box_sharded_refine_and_row_sharded_iou(tmp_path):
+    from boxfusion_b200.sharding import block_range
+    assert [block_range(5, r, 2) for r in range(2)] == [(0, 3), (3, 5)]
+    assert [block_range(3, r, 8) for r in range(8)] == [(0, 1), (1, 2), (2, 3)] + [(3, 3)] * 5
+    covered = [i for r in range(8) for i in range(*block_range(128, r, 8))]
+    assert covered == list(range(128))
+    port_no = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_step, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "step.npz")
+    from oracle import port
+    prob, uv, pst, K16, cs, B, V = _refine_inputs()
+    fn = _oracle_refine_fn(K16, cs)
+    off = np.arange(B + 1, dtype=np.int32) * V
+    out, upd, its = fn(pst, prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 3, 3), prob["scores"].reshape(-1),
+                       uv.reshape(-1, 16), prob["poses"].reshape(-1, 4, 4), off, np.arange(B * V, dtype=np.int32), None)
+    assert np.array_equal(got["out"].view(np.uint32), out.numpy().view(np.uint32))
+    assert np.array_equal(got["upd"], upd.numpy()) and np.array_equal(got["its"], its.numpy())
+    port.IOU_BACKEND = "c"
+    ca = port.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][:, 0]), torch.from_numpy(prob["R"][:, 0])).corners.numpy()
+    cb = port.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][:, 1]), torch.from_numpy(prob["R"][:, 1])).corners.numpy()
+    exp = np.stack([port.calculate_obb_iou(x, cb) for x in ca])
+    assert got["iou"].shape == (B, B) and np.array_equal(got["iou"], exp)
