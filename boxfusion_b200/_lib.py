@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("BOXFUSION_B200_LIB") or os.path.join(_HERE, "lib", "l
 BF_OK, BF_ERR_INVALID_ARG, BF_ERR_CUDA, BF_ERR_CAPACITY = 0, -1, -2, -3
 IOU_SAMPLED_REF, IOU_ANALYTIC = 0, 1
 OPT_REFINE_CONCURRENT = 1
+OPT_REFINE_PERSISTENT = 2
 _ERR = {-1: "BF_ERR_INVALID_ARG", -2: "BF_ERR_CUDA", -3: "BF_ERR_CAPACITY"}
 
 _vp, _i32, _f32, _f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
@@ -49,7 +50,31 @@ class FusedTable(ctypes.Structure):
     _fields_ = [("lists", _vp), ("len", _vp), ("hash", _vp), ("count", _vp), ("cap", ctypes.c_int32)]
 
 
-_MBP, _SBP, _FTP = ctypes.POINTER(MapBuffers), ctypes.POINTER(StoreBuffers), ctypes.POINTER(FusedTable)
+class EngineCfg(ctypes.Structure):
+    """bf_engine_cfg"""
+    _fields_ = [("map_capacity", ctypes.c_int32), ("store_capacity", ctypes.c_int32), ("max_det", ctypes.c_int32),
+                ("iou_mode", ctypes.c_int32), ("nms_threshold", _f64), ("small_threshold", _f64),
+                ("translation_gap", _f32), ("rotation_gap", _f32), ("center_gap", _f32),
+                ("small_size", _f32), ("small_plus", _f32),
+                ("use_fusion", ctypes.c_int32), ("check_valid", ctypes.c_int32), ("gap", ctypes.c_int32), ("use_graph", ctypes.c_int32),
+                ("refine", RefineCfg), ("pst", _vp), ("P", ctypes.c_int32)]
+
+
+class EngineBuffers(ctypes.Structure):
+    """bf_engine_buffers"""
+    _fields_ = [("map", MapBuffers * 2), ("store", StoreBuffers), ("fusion_flag", _vp), ("fused", FusedTable)]
+
+
+class EngineState(ctypes.Structure):
+    """bf_engine_state (32 x int32)"""
+    _fields_ = [(k, ctypes.c_int32) for k in ("N", "M", "cur", "steps", "n", "Nall", "Nnms", "first", "any_new", "Nnew", "B", "SV", "maxV")] + \
+               [("status", ctypes.c_int32 * 8), ("refine_boxes_total", ctypes.c_int32), ("refine_views_total", ctypes.c_int32),
+                ("pad", ctypes.c_int32 * 9)]
+
+
+KF_HEADER, KF_ROW = 56, 22
+PH_INGEST, PH_NMS, PH_CORR, PH_COMPACT, PH_VALID, PH_FUSE, PH_FINISH = (1 << i for i in range(7))
+_ESP = ctypes.POINTER(EngineState)
 
 # name -> (restype, argtypes); every symbol declared in include/boxfusion_b200.h
 PROTOTYPES = {
@@ -70,12 +95,18 @@ PROTOTYPES = {
     "bf_pose_disparity": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bf_refine": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, ctypes.POINTER(RefineCfg),
                          _vp, _vp, _vp, _vp, _vp, _vp]),
-    "bf_engine_ingest": (_i32, [_vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _i32, _i32, _MBP, _SBP, _vp, _vp]),
-    "bf_engine_corr": (_i32, [_vp, _MBP, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f64,
-                              _f32, _f32, _vp, _vp, _vp]),
-    "bf_engine_compact": (_i32, [_vp, _vp, _i32, _MBP, _MBP, _vp, _vp]),
-    "bf_engine_select": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp]),
-    "bf_engine_apply": (_i32, [_vp, _MBP, _FTP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bf_engine_create": (_i32, [_i32, ctypes.POINTER(EngineCfg), ctypes.POINTER(EngineBuffers), ctypes.POINTER(_vp)]),
+    "bf_engine_destroy": (None, [_vp]),
+    "bf_engine_last_error": (ctypes.c_char_p, [_vp]),
+    "bf_engine_reset": (_i32, [_vp, _vp]),
+    "bf_engine_step": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "bf_engine_step_device": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "bf_engine_ingest_world": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "bf_engine_set_counts": (_i32, [_vp, _i32, _i32, _vp]),
+    "bf_engine_read_state": (_i32, [_vp, _ESP, _vp]),
+    "bf_engine_read_flags": (_i32, [_vp, _vp, _vp, _i32, _ESP, _vp]),
+    "bf_engine_pointers": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "bf_engine_launch_counts": (_i32, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     "bf_detection_filter": (_i32, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _f64, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
     "bf_set_option": (_i32, [_vp, _i32, _i32]),

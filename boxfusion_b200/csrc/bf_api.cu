@@ -26,6 +26,7 @@ extern "C" int bf_create(int device, bf_handle** out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     { const char* t = getenv("BF_REFINE_TIMING"); h->refine_timing = (t && (t[0] == '1' || t[0] == '2')) ? (t[0] - '0') : 0; }
+    { const char* t = getenv("BF_REFINE_PERSISTENT"); h->refine_force_persistent = t ? atoi(t) : 0; }
     { const char* t = getenv("BF_REFINE_SHAPE"); h->refine_force_variant = -1; if (t) sscanf(t, "%d,%d,%d", &h->refine_force_c, &h->refine_force_t, &h->refine_force_variant); }
     *out = h;
     return BF_OK;
@@ -34,6 +35,7 @@ extern "C" int bf_create(int device, bf_handle** out) {
 extern "C" int bf_set_option(bf_handle* h, int key, int value) {
     if (!h) return BF_ERR_INVALID_ARG;
     if (key == BF_OPT_REFINE_CONCURRENT) { h->refine_concurrent = value ? 1 : 0; return BF_OK; }
+    if (key == BF_OPT_REFINE_PERSISTENT) { h->refine_force_persistent = value > 0 ? value : 0; return BF_OK; }
     return bf_fail(h, BF_ERR_INVALID_ARG, "bf_set_option", "unknown key");
 }
 

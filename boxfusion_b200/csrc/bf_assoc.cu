@@ -4,123 +4,110 @@
 // scoring for small objects (instances.py:446-468, 643-717).
 #include "bf_common.cuh"
 
-int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* cornersB, int N, int triangle, int mode,
-                 double* iou, int32_t* counts, int64_t* stats, double thr, const int32_t* rank, uint32_t* mask,
-                 uint32_t* rowany, int W, unsigned long long* edges, int edge_cap, cudaStream_t st);
-int bf_iou3d_overflowed(bf_handle* h, cudaStream_t st, int* overflow);
+#include "bf_internal.cuh"
+#include "bf_record.cuh"
 
-__global__ void bf_rank_kernel(const int32_t* __restrict__ order, int N, int32_t* __restrict__ rank) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < N) rank[order[r]] = r;
+__global__ void bf_rank_kernel(const int32_t* __restrict__ order, const bf_dimref Nd, int32_t* __restrict__ rank) {
+    const int N = bf_dim(Nd);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) rank[order[r]] = r;
 }
 
 // ---- score order of nms_3d (instances.py:52) ---------------------------------------------------------------------
-// 64-bit keys (descending score, ascending index) sorted ascending by a bitonic network in shared memory.
-#define BF_ORDER_MAX 4096
-__global__ void __launch_bounds__(1024)
-bf_score_order_kernel(const float* __restrict__ scores, int N, int n_pad, int32_t* __restrict__ order) {
-    extern __shared__ unsigned long long bf_keys[];
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        unsigned long long k = ~0ull;                                   // padding sorts last
-        if (i < N) {
-            float f = scores[i];
-            unsigned u;
-            if (f != f) u = 0xffffffffu;                                // NaN: greater than everything (torch's order)
-            else {
-                if (f == 0.0f) f = 0.0f;                                // -0 == +0
-                const unsigned b = __float_as_uint(f);
-                u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);         // monotone float -> unsigned
-            }
-            k = ((unsigned long long)(~u) << 32) | (unsigned)i;        // descending score, then ascending index
-        }
-        bf_keys[i] = k;
+// 64-bit keys (descending score, ascending index), unique per box.  N <= 4096: block 0 sorts them ascending with a
+// bitonic network in shared memory.  Larger N (the 4 352-box stress map of BASELINE configs[2], engine maps up to
+// 65 536 rows): every block ranks its boxes by counting the smaller keys, tile by tile through shared memory -
+// O(N^2) compares like the pair stage of the NMS it feeds, no multi-pass global sort, fixed launch shape.
+#define BF_ORDER_SMEM 4096
+__device__ __forceinline__ unsigned long long bf_score_key(float f, int i) {
+    unsigned u;
+    if (f != f) u = 0xffffffffu;                                // NaN: greater than everything (torch's order)
+    else {
+        if (f == 0.0f) f = 0.0f;                                // -0 == +0
+        const unsigned b = __float_as_uint(f);
+        u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);         // monotone float -> unsigned
     }
-    __syncthreads();
-    for (int size = 2; size <= n_pad; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
-                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const unsigned long long a = bf_keys[lo], b = bf_keys[hi];
-                if ((a > b) == up) { bf_keys[lo] = b; bf_keys[hi] = a; }
-            }
-            __syncthreads();
-        }
-    for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = (int32_t)(bf_keys[i] & 0xffffffffull);
+    return ((unsigned long long)(~u) << 32) | (unsigned)i;      // descending score, then ascending index
 }
 
-extern "C" int bf_score_order(bf_handle* h, const float* scores, int N, int32_t* order, void* stream) {
-    if (!h || N < 0 || N > BF_ORDER_MAX || (N > 0 && (!scores || !order))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_score_order", "bad argument");
-    if (N == 0) return BF_OK;
-    int n_pad = 2;
-    while (n_pad < N) n_pad <<= 1;
-    const int threads = n_pad / 2 < 1024 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 1024;
-    bf_score_order_kernel<<<1, threads, sizeof(unsigned long long) * (size_t)n_pad, (cudaStream_t)stream>>>(scores, N, n_pad, order);
+__global__ void __launch_bounds__(1024)
+bf_score_order_kernel(const float* __restrict__ scores, const bf_dimref Nd, int32_t* __restrict__ order, int32_t* __restrict__ rank) {
+    __shared__ unsigned long long bf_keys[BF_ORDER_SMEM];
+    const int N = bf_dim(Nd);
+    if (N <= BF_ORDER_SMEM) {
+        if (blockIdx.x != 0 || N <= 0) return;
+        int n_pad = 2;
+        while (n_pad < N) n_pad <<= 1;
+        for (int i = threadIdx.x; i < n_pad; i += blockDim.x) bf_keys[i] = (i < N) ? bf_score_key(scores[i], i) : ~0ull;   // padding sorts last
+        __syncthreads();
+        for (int size = 2; size <= n_pad; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                    const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const bool up = ((lo & size) == 0);
+                    const unsigned long long a = bf_keys[lo], b = bf_keys[hi];
+                    if ((a > b) == up) { bf_keys[lo] = b; bf_keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int idx = (int)(bf_keys[i] & 0xffffffffull);
+            order[i] = idx;
+            if (rank) rank[idx] = i;
+        }
+        return;
+    }
+    // rank by counting: box i goes to position #{j : key_j < key_i}
+    const int per_pass = gridDim.x * blockDim.x;
+    for (int base = 0; base < N; base += per_pass) {                 // block-uniform trip count
+        const int i = base + blockIdx.x * blockDim.x + threadIdx.x;
+        const unsigned long long ki = (i < N) ? bf_score_key(scores[i], i) : 0ull;
+        int cnt = 0;
+        for (int t0 = 0; t0 < N; t0 += BF_ORDER_SMEM) {
+            __syncthreads();
+            for (int j = threadIdx.x; j < BF_ORDER_SMEM; j += blockDim.x) bf_keys[j] = (t0 + j < N) ? bf_score_key(scores[t0 + j], t0 + j) : ~0ull;
+            __syncthreads();
+            const int lim = min(BF_ORDER_SMEM, N - t0);
+#pragma unroll 8
+            for (int j = 0; j < lim; ++j) cnt += (bf_keys[j] < ki) ? 1 : 0;
+        }
+        if (i < N) { order[cnt] = i; if (rank) rank[i] = cnt; }
+    }
+}
+
+int bf_score_order_run(bf_handle* h, const float* scores, bf_dimref Nd, int32_t* order, int32_t* rank, cudaStream_t st) {
+    const int blocks = Nd.host <= BF_ORDER_SMEM ? 1 : (bf_blocks(Nd.host, 1024) < h->sm_count ? bf_blocks(Nd.host, 1024) : h->sm_count);
+    bf_score_order_kernel<<<blocks, 1024, 0, st>>>(scores, Nd, order, rank);
     BF_LAUNCH_CHECK(h, "bf_score_order_kernel");
     return BF_OK;
 }
 
-// box_manager.py:188-215 with the test of :55 / :71
-__device__ __forceinline__ bool bf_views_differ(const float* __restrict__ p1, const float* __restrict__ p2,
-                                                float translation_gap, float rotation_gap, bool use_center,
-                                                float center_dis, float center_gap) {
-    const float dx = p2[3] - p1[3], dy = p2[7] - p1[7], dz = p2[11] - p1[11];
-    const float baseline = sqrtf(dx * dx + dy * dy + dz * dz);
-    float tr = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) tr += p2[4 * r] * p1[4 * r] + p2[4 * r + 1] * p1[4 * r + 1] + p2[4 * r + 2] * p1[4 * r + 2];
-    const float c = fminf(fmaxf((tr - 1.f) * 0.5f, -1.f), 1.f);
-    const float angle = acosf(c) * 180.f / 3.14159265358979323846f;
-    return (baseline > translation_gap || angle > rotation_gap) || (use_center && center_dis > center_gap);
+extern "C" int bf_score_order(bf_handle* h, const float* scores, int N, int32_t* order, void* stream) {
+    bf_device_guard guard(h);
+    if (!h || N < 0 || N > 65536 || (N > 0 && (!scores || !order))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_score_order", "bad argument");
+    if (N == 0) return BF_OK;
+    return bf_score_order_run(h, scores, bf_dim_host(N), order, nullptr, (cudaStream_t)stream);
 }
 
-// sorted insert of `val` into list[0..len) (ascending; duplicates kept, like list.sort())
-__device__ __forceinline__ void bf_sorted_insert(int32_t* list, int& len, int32_t val) {
-    int k = len;
-    while (k > 0 && list[k - 1] > val) { list[k] = list[k - 1]; --k; }
-    list[k] = val;
-    ++len;
-}
-
-// BoxManager.record for one suppressed box `idx` of head `cur` (box_manager.py:48-86).  lc/len_c: the head's list.
-struct bf_record_ctx {
-    const int32_t* order; const int32_t* init_id; const float* poses; const float* centers;
-    int32_t* fl; int32_t* flen; int32_t* fflag; int32_t* keep; int32_t* status;
-    float translation_gap, rotation_gap, center_gap;
-};
-
-__device__ __forceinline__ void bf_record_one(const bf_record_ctx& c, int cur, int idx, int32_t* lc, int& len_c,
-                                              bool& cur_in_keep) {
-    const float* cc = c.centers + 3 * cur;
-    const float* ci = c.centers + 3 * idx;
-    const float ex = cc[0] - ci[0], ey = cc[1] - ci[1], ez = cc[2] - ci[2];
-    const float cdis = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
-    const int len_i = c.flen[idx];
-    const int32_t* li = c.fl + (size_t)idx * BF_FUSION_CAP;
-    if (len_i == 1) {                                     // box_manager.py:50-62
-        const float* pi = c.poses + 16 * (size_t)c.init_id[idx];
-        int cnt = 0;
-        for (int k = 0; k < len_c; ++k)
-            cnt += bf_views_differ(c.poses + 16 * (size_t)lc[k], pi, c.translation_gap, c.rotation_gap, true, cdis, c.center_gap);
-        if (cnt == len_c && len_c < 5) {
-            if (len_c + 1 > BF_FUSION_CAP) c.status[0] = BF_ERR_CAPACITY;
-            else bf_sorted_insert(lc, len_c, c.init_id[idx]);
-        }
-    } else {                                              // box_manager.py:65-86
-        const float* pc = c.poses + 16 * (size_t)c.init_id[cur];
-        int cnt = 0;
-        for (int k = 0; k < len_i; ++k)
-            cnt += bf_views_differ(c.poses + 16 * (size_t)li[k], pc, c.translation_gap, c.rotation_gap, true, cdis, c.center_gap);
-        if (cnt == len_i && len_i < 5) {
-            if (len_c + len_i > BF_FUSION_CAP) c.status[0] = BF_ERR_CAPACITY;
-            else for (int k = 0; k < len_i; ++k) bf_sorted_insert(lc, len_c, li[k]);
-        } else if (cur_in_keep) {                         // swap: keep.remove(cur); keep.append(idx)
+// record() of one head over its live partners, in descending score order (instances.py:72-85).  `keys` is a list of
+// (head rank << 32 | partner rank) sorted ascending, `first` the head's first entry; entries with act[g] == 0 are skipped.
+__device__ __forceinline__ void bf_record_head(const bf_record_ctx& ctx, const unsigned long long* keys, const unsigned char* act,
+                                               int first, int E, int32_t* __restrict__ success) {
+    const int r0 = (int)(keys[first] >> 32);
+    const int cur = ctx.order[r0];
+    int32_t* lc = ctx.fl + (size_t)cur * BF_FUSION_CAP;
+    int len_c = ctx.flen[cur];
+    bool cur_in_keep = true, any = false;
+    for (int g = first; g < E && (int)(keys[g] >> 32) == r0; ++g) {
+        if (act && !act[g]) continue;
+        any = true;
+        const int idx = ctx.order[(int)(keys[g] & 0xffffffffu)];
+        if (bf_record_one(ctx, cur, idx, lc, len_c) && cur_in_keep) {   // swap: keep.remove(cur); keep.append(idx)
             cur_in_keep = false;
-            c.keep[idx] = 1;                              // forced keep
-            c.keep[cur] = -1;                             // dropped
+            ctx.keep[idx] = 1;                            // forced keep
+            ctx.keep[cur] = -1;                           // dropped
         }
-        if (c.fflag[idx] == 1) c.fflag[cur] = 1;
     }
+    if (any) { success[cur] = 1; ctx.flen[cur] = len_c; }
 }
 
 // Sparse greedy matching (the common case: few over-threshold pairs).  The IoU kernels emit one edge
@@ -128,21 +115,26 @@ __device__ __forceinline__ void bf_record_one(const bf_record_ctx& c, int cur, i
 // decide which (head, partner) pairs are live - nms_3d's loop (instances.py:58-97) touches nothing else - and then
 // record() runs in parallel over heads: calls of different heads write disjoint lists/flags and only read lists of
 // suppressed boxes, which never change.  Falls through (returns) when the edge list overflowed; the dense kernel
-// below handles that case.
+// below handles that case.  status is sticky (never cleared here): the caller zeroes it.
 #define BF_EDGE_CAP 8192
 __global__ void __launch_bounds__(1024)
 bf_greedy_edges_kernel(const unsigned long long* __restrict__ edges, const unsigned long long* __restrict__ counters,
-                       int N, int W, bf_record_ctx ctx, int32_t* __restrict__ success) {
+                       const bf_dimref Nd, int have_dense, bf_record_ctx ctx, int32_t* __restrict__ success) {
     extern __shared__ unsigned long long s_keys[];
+    const int N = bf_dim(Nd);
+    const int W = (N + 31) >> 5;
     const unsigned long long E64 = counters[6];
-    if (E64 > BF_EDGE_CAP) return;
-    const int E = (int)E64, tid = threadIdx.x, T = blockDim.x;
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (E64 > BF_EDGE_CAP) {
+        if (!have_dense && tid == 0) atomicExch(ctx.status, BF_ERR_CAPACITY);   // no dense mask for maps this large
+        return;
+    }
+    const int E = (int)E64;
     int n2 = 1;
     while (n2 < E) n2 <<= 1;
     uint32_t* remaining = (uint32_t*)(s_keys + n2);
     unsigned char* act = (unsigned char*)(remaining + W);
     for (int i = tid; i < N; i += T) { ctx.keep[i] = 0; success[i] = 0; }
-    if (tid == 0) ctx.status[0] = 0;
     for (int i = tid; i < n2; i += T) s_keys[i] = (i < E) ? edges[i] : ~0ULL;
     for (int w = tid; w < W; w += T) {
         const int base = w << 5;
@@ -173,18 +165,8 @@ bf_greedy_edges_kernel(const unsigned long long* __restrict__ edges, const unsig
     }
     __syncthreads();
     for (int e = tid; e < E; e += T) {                     // one thread per head: record() over its live partners, in order
-        const int r0 = (int)(s_keys[e] >> 32);
-        if (e > 0 && (int)(s_keys[e - 1] >> 32) == r0) continue;
-        const int cur = ctx.order[r0];
-        int32_t* lc = ctx.fl + (size_t)cur * BF_FUSION_CAP;
-        int len_c = ctx.flen[cur];
-        bool cur_in_keep = true, any = false;
-        for (int g = e; g < E && (int)(s_keys[g] >> 32) == r0; ++g) {
-            if (!act[g]) continue;
-            any = true;
-            bf_record_one(ctx, cur, ctx.order[(int)(s_keys[g] & 0xffffffffu)], lc, len_c, cur_in_keep);
-        }
-        if (any) { success[cur] = 1; ctx.flen[cur] = len_c; }
+        if (e > 0 && (int)(s_keys[e - 1] >> 32) == (int)(s_keys[e] >> 32)) continue;
+        bf_record_head(ctx, s_keys, act, e, E, success);
     }
     __syncthreads();
     for (int r = tid; r < N; r += T) {                     // keep = never suppressed, minus dropped heads, plus forced keeps
@@ -195,134 +177,116 @@ bf_greedy_edges_kernel(const unsigned long long* __restrict__ edges, const unsig
     }
 }
 
-// Dense fallback (edge list overflowed).  One warp.  Walks, in ascending score rank, the heads that have at least one over-threshold partner;
-// every other box is kept untouched.  Lane 0 performs record(); the other lanes help with the bit-mask rows.
-__global__ void __launch_bounds__(32)
-bf_greedy_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ rowany, int N, int W,
-                 const int32_t* __restrict__ order, const int32_t* __restrict__ init_id,
-                 const float* __restrict__ poses, int M, const float* __restrict__ centers,
-                 int32_t* __restrict__ fl, int32_t* __restrict__ flen, int32_t* __restrict__ fflag,
-                 float translation_gap, float rotation_gap, float center_gap,
-                 int32_t* __restrict__ keep, int32_t* __restrict__ success, int32_t* __restrict__ status,
-                 const unsigned long long* __restrict__ counters) {
+// Dense fallback (edge list overflowed): the rank-space bit mask read row by row IS the sorted edge list.  Warp 0 walks,
+// in ascending score rank, the heads that have at least one over-threshold partner (every other box is kept untouched)
+// and writes the LIVE (head, partner) pairs - at most one per box, a box is suppressed once - to `live`; then record()
+// runs in parallel over heads exactly as in the sparse kernel.
+__global__ void __launch_bounds__(1024)
+bf_greedy_dense_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ rowany, const bf_dimref Nd,
+                       bf_record_ctx ctx, int32_t* __restrict__ success, const unsigned long long* __restrict__ counters,
+                       unsigned long long* __restrict__ live) {
     extern __shared__ uint32_t s_mem[];
     if (counters[6] <= BF_EDGE_CAP) return;              // bf_greedy_edges_kernel handled this call
+    const int N = bf_dim(Nd);
+    const int W = (N + 31) >> 5;
     uint32_t* remaining = s_mem;            // [W] ranks not yet suppressed
-    uint32_t* sup = s_mem + W;              // [W] scratch: suppressed by the current head
-    const int lane = threadIdx.x;
-    for (int w = lane; w < W; w += 32) {
+    __shared__ int s_E;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    for (int w = tid; w < W; w += T) {
         const int base = w << 5;
         remaining[w] = (base + 32 <= N) ? 0xffffffffu : ((base < N) ? ((1u << (N - base)) - 1u) : 0u);
     }
-    for (int i = lane; i < N; i += 32) { keep[i] = 0; success[i] = 0; }
-    if (lane == 0) status[0] = 0;
-    __syncwarp();
-    for (int hw = 0; hw < W; ++hw) {
-        uint32_t heads = rowany[hw];
-        while (heads) {
-            const int bit = __ffs(heads) - 1;
-            heads &= heads - 1;
-            const int r = (hw << 5) + bit;
-            if (!((remaining[hw] >> bit) & 1u)) continue;                  // suppressed earlier: never a head
-            bool any = false;
-            for (int w = lane; w < W; w += 32) {
-                const uint32_t s = mask[(size_t)r * W + w] & remaining[w];
-                sup[w] = s;
-                any |= (s != 0);
-            }
-            any = __any_sync(0xffffffffu, any);
-            __syncwarp();
-            if (!any) continue;
-            const int cur = order[r];
-            if (lane == 0) {
-                success[cur] = 1;                                            // instances.py:72-83
-                bool cur_in_keep = true;
-                int32_t* lc = fl + (size_t)cur * BF_FUSION_CAP;
-                int len_c = flen[cur];
-                const float* cc = centers + 3 * cur;
-                for (int w = 0; w < W; ++w) {
-                    uint32_t s = sup[w];
-                    while (s) {
-                        const int b2 = __ffs(s) - 1;
-                        s &= s - 1;
-                        const int idx = order[(w << 5) + b2];                 // descending score order (:85)
-                        const float* ci = centers + 3 * idx;
-                        const float ex = cc[0] - ci[0], ey = cc[1] - ci[1], ez = cc[2] - ci[2];
-                        const float cdis = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
-                        const int len_i = flen[idx];
-                        const int32_t* li = fl + (size_t)idx * BF_FUSION_CAP;
-                        if (len_i == 1) {                                     // box_manager.py:50-62
-                            const float* pi = poses + 16 * (size_t)init_id[idx];
-                            int cnt = 0;
-                            for (int k = 0; k < len_c; ++k)
-                                cnt += bf_views_differ(poses + 16 * (size_t)lc[k], pi, translation_gap, rotation_gap, true, cdis, center_gap);
-                            if (cnt == len_c && len_c < 5) {
-                                if (len_c + 1 > BF_FUSION_CAP) status[0] = BF_ERR_CAPACITY;
-                                else bf_sorted_insert(lc, len_c, init_id[idx]);
-                            }
-                        } else {                                              // box_manager.py:65-86
-                            const float* pc = poses + 16 * (size_t)init_id[cur];
-                            int cnt = 0;
-                            for (int k = 0; k < len_i; ++k)
-                                cnt += bf_views_differ(poses + 16 * (size_t)li[k], pc, translation_gap, rotation_gap, true, cdis, center_gap);
-                            if (cnt == len_i && len_i < 5) {
-                                if (len_c + len_i > BF_FUSION_CAP) status[0] = BF_ERR_CAPACITY;
-                                else for (int k = 0; k < len_i; ++k) bf_sorted_insert(lc, len_c, li[k]);
-                            } else if (cur_in_keep) {                         // swap: keep.remove(cur); keep.append(idx)
-                                cur_in_keep = false;
-                                keep[idx] = 1;                                // forced keep
-                                keep[cur] = -1;                               // dropped
-                            }
-                            if (fflag[idx] == 1) fflag[cur] = 1;
-                        }
+    for (int i = tid; i < N; i += T) { ctx.keep[i] = 0; success[i] = 0; }
+    __syncthreads();
+    if (tid < 32) {
+        int E = 0;
+        for (int hw = 0; hw < W; ++hw) {
+            uint32_t heads = rowany[hw];
+            while (heads) {
+                const int bit = __ffs(heads) - 1;
+                heads &= heads - 1;
+                const int r = (hw << 5) + bit;
+                if (!((remaining[hw] >> bit) & 1u)) continue;                  // suppressed earlier: never a head
+                for (int w0 = 0; w0 < W; w0 += 32) {                            // partners in ascending rank = descending score (:85)
+                    const int w = w0 + lane;
+                    const uint32_t s = (w < W) ? (mask[(size_t)r * W + w] & remaining[w]) : 0u;
+                    const int c = __popc(s);
+                    int incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                    int pos = E + incl - c;
+                    uint32_t q = s;
+                    while (q) {
+                        const int b2 = __ffs(q) - 1;
+                        q &= q - 1;
+                        live[pos++] = ((unsigned long long)r << 32) | (unsigned long long)((w << 5) + b2);
                     }
+                    if (w < W) remaining[w] &= ~s;
+                    E += __shfl_sync(0xffffffffu, incl, 31);
                 }
-                flen[cur] = len_c;
+                __syncwarp();
             }
-            __syncwarp();
-            for (int w = lane; w < W; w += 32) remaining[w] &= ~sup[w];
-            __syncwarp();
         }
+        if (lane == 0) s_E = E;
     }
-    __syncwarp();
-    // keep = never-suppressed ranks, minus dropped heads, plus forced keeps
-    for (int r = lane; r < N; r += 32) {
-        const int i = order[r];
+    __syncthreads();
+    const int E = s_E;
+    __threadfence_block();
+    for (int e = tid; e < E; e += T) {
+        if (e > 0 && (int)(live[e - 1] >> 32) == (int)(live[e] >> 32)) continue;
+        bf_record_head(ctx, live, nullptr, e, E, success);
+    }
+    __syncthreads();
+    for (int r = tid; r < N; r += T) {
+        const int i = ctx.order[r];
         const bool rem = (remaining[r >> 5] >> (r & 31)) & 1u;
-        const int k = keep[i];
-        keep[i] = (k == 1) ? 1 : ((k == -1) ? 0 : (rem ? 1 : 0));
+        const int k = ctx.keep[i];
+        ctx.keep[i] = (k == 1) ? 1 : ((k == -1) ? 0 : (rem ? 1 : 0));
     }
 }
 
-extern "C" int bf_nms3d(bf_handle* h, const float* corners, const float* centers, int N, const int32_t* order,
-                        const int32_t* init_id, const float* poses, int M, int32_t* fusion_list, int32_t* fusion_len,
-                        int32_t* fusion_flag, double iou_threshold, float translation_gap, float rotation_gap_deg,
-                        float center_gap, int mode, int32_t* keep, int32_t* success, int32_t* status, void* stream) {
-    if (!h || N < 0 || M < 0) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d", "bad size");
-    if (N == 0) return BF_OK;
-    if (!corners || !centers || !order || !init_id || !poses || !fusion_list || !fusion_len || !fusion_flag || !keep ||
-        !success || !status)
-        return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d", "null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
+#define BF_DENSE_MASK_MAX_N 16384      // the dense rank-space mask (N x N/32 words) is kept for maps up to this size
+
+// nms_3d + record() from corners / centres / score order.  Nd: the box count on the host, or its bound on the host and the
+// count itself in device memory.  All scratch comes from the handle (sized for Nd.host).  status is OR-ed into, never cleared.
+int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_dimref Nd, const int32_t* order, int32_t* rank_or_null,
+                 const int32_t* init_id, const float* poses, int32_t* fusion_list, int32_t* fusion_len, int32_t* fusion_flag,
+                 double iou_threshold, float translation_gap, float rotation_gap_deg, float center_gap, int mode,
+                 int32_t* keep, int32_t* success, int32_t* status, cudaStream_t st) {
+    const int N = Nd.host;
     const int W = (N + 31) / 32;
-    if ((size_t)2 * W * sizeof(uint32_t) > 200 * 1024) return bf_fail(h, BF_ERR_CAPACITY, "bf_nms3d", "N too large for the greedy kernel");
+    const bool dense = N <= BF_DENSE_MASK_MAX_N;
     void* p;
     int rc;
-    if ((rc = bf_scratch(h, BF_SCRATCH_MASK, sizeof(uint32_t) * ((size_t)N * W + W), &p))) return rc;
-    uint32_t* mask = (uint32_t*)p;
-    uint32_t* rowany = mask + (size_t)N * W;
-    if ((rc = bf_scratch(h, BF_SCRATCH_RANK, sizeof(int32_t) * (size_t)N, &p))) return rc;
-    int32_t* rank = (int32_t*)p;
+    uint32_t *mask = nullptr, *rowany = nullptr;
+    if (dense) {
+        if ((rc = bf_scratch(h, BF_SCRATCH_MASK, sizeof(uint32_t) * ((size_t)N * W + W) + sizeof(unsigned long long) * (size_t)(N + 1), &p))) return rc;
+        mask = (uint32_t*)p;
+    }
+    int32_t* rank = rank_or_null;
+    if (!rank) {
+        if ((rc = bf_scratch(h, BF_SCRATCH_RANK, sizeof(int32_t) * (size_t)N, &p))) return rc;
+        rank = (int32_t*)p;
+    }
     if ((rc = bf_scratch(h, BF_SCRATCH_EDGES, sizeof(unsigned long long) * BF_EDGE_CAP, &p))) return rc;
     unsigned long long* edges = (unsigned long long*)p;
+    unsigned long long* live = nullptr;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        BF_CUDA(h, cudaMemsetAsync(mask, 0, sizeof(uint32_t) * ((size_t)N * W + W), st));
-        bf_rank_kernel<<<bf_blocks(N, 128), 128, 0, st>>>(order, N, rank);
-        BF_LAUNCH_CHECK(h, "bf_rank_kernel");
-        if ((rc = bf_iou3d_run(h, corners, N, corners, N, 1, mode, nullptr, nullptr, nullptr, iou_threshold, rank, mask,
-                               rowany, W, edges, BF_EDGE_CAP, st)))
+        if (dense) {
+            // the mask rows are laid out with the stride of the ACTUAL box count (<= the bound); rowany and the live list sit
+            // behind the rows of the bound, so their addresses do not depend on the actual count
+            BF_CUDA(h, cudaMemsetAsync(mask, 0, sizeof(uint32_t) * ((size_t)N * W + W), st));
+            rowany = mask + (size_t)N * W;
+            live = (unsigned long long*)(mask + (((size_t)N * W + W + 1) & ~(size_t)1));
+        }
+        if (!rank_or_null) {
+            bf_rank_kernel<<<bf_blocks(N, 128) < 64 ? bf_blocks(N, 128) : 64, 128, 0, st>>>(order, Nd, rank);
+            BF_LAUNCH_CHECK(h, "bf_rank_kernel");
+        }
+        if ((rc = bf_iou3d_run(h, corners, Nd, corners, Nd, 1, mode, nullptr, nullptr, nullptr, iou_threshold, rank, mask,
+                               rowany, edges, BF_EDGE_CAP, st)))
             return rc;
-        if ((long long)N * N <= (long long)(h->cap[BF_SCRATCH_WORK] / 8)) break;
+        if (Nd.dev || (long long)N * N <= (long long)(h->cap[BF_SCRATCH_WORK] / 8)) break;   // cannot overflow / checked by the engine's status word
         int ovf = 0;
         if ((rc = bf_iou3d_overflowed(h, st, &ovf))) return rc;
         if (!ovf) break;
@@ -337,17 +301,29 @@ extern "C" int bf_nms3d(bf_handle* h, const float* corners, const float* centers
     // sparse path: sorted edge list in shared memory (keys + remaining bit set + live flags)
     const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
     BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-    bf_greedy_edges_kernel<<<1, 1024, smem_e, st>>>(edges, counters, N, W, ctx, success);
+    bf_greedy_edges_kernel<<<1, 1024, smem_e, st>>>(edges, counters, Nd, dense ? 1 : 0, ctx, success);
     BF_LAUNCH_CHECK(h, "bf_greedy_edges_kernel");
-    // dense fallback: returns immediately unless the edge list overflowed
-    const size_t smem = sizeof(uint32_t) * 2 * (size_t)W;
-    if (smem > 48 * 1024)
-        BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bf_greedy_kernel<<<1, 32, smem, st>>>(mask, rowany, N, W, order, init_id, poses, M, centers, fusion_list, fusion_len,
-                                          fusion_flag, translation_gap, rotation_gap_deg, center_gap, keep, success, status,
-                                          counters);
-    BF_LAUNCH_CHECK(h, "bf_greedy_kernel");
+    if (dense) {
+        // dense fallback: returns immediately unless the edge list overflowed
+        const size_t smem = sizeof(uint32_t) * (size_t)W + 16;
+        bf_greedy_dense_kernel<<<1, 1024, smem, st>>>(mask, rowany, Nd, ctx, success, counters, live);
+        BF_LAUNCH_CHECK(h, "bf_greedy_dense_kernel");
+    }
     return BF_OK;
+}
+
+extern "C" int bf_nms3d(bf_handle* h, const float* corners, const float* centers, int N, const int32_t* order,
+                        const int32_t* init_id, const float* poses, int M, int32_t* fusion_list, int32_t* fusion_len,
+                        int32_t* fusion_flag, double iou_threshold, float translation_gap, float rotation_gap_deg,
+                        float center_gap, int mode, int32_t* keep, int32_t* success, int32_t* status, void* stream) {
+    bf_device_guard guard(h);
+    if (!h || N < 0 || M < 0 || N > 65536) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d", "bad size");
+    if (N == 0) return BF_OK;
+    if (!corners || !centers || !order || !init_id || !poses || !fusion_list || !fusion_len || !fusion_flag || !keep ||
+        !success || !status)
+        return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d", "null pointer");
+    return bf_nms3d_run(h, corners, centers, bf_dim_host(N), order, nullptr, init_id, poses, fusion_list, fusion_len, fusion_flag,
+                        iou_threshold, translation_gap, rotation_gap_deg, center_gap, mode, keep, success, status, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -413,6 +389,7 @@ __global__ void bf_corr_match_kernel(const double* __restrict__ boxes2d, const i
 extern "C" int bf_corr2d(bf_handle* h, const float* map_corners, const int32_t* small_mask, int G, const float* pose_inv,
                          float fx, float fy, float cx, float cy, float W, float H, const float* det_xyxy, int n_small,
                          double* boxes2d, int32_t* best, double* best_iou, void* stream) {
+    bf_device_guard guard(h);
     if (!h || G < 0 || n_small < 0) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_corr2d", "bad size");
     if (n_small == 0) return BF_OK;
     if (!best || !best_iou || !det_xyxy || !pose_inv || (G > 0 && (!map_corners || !small_mask)))

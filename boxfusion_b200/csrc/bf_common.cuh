@@ -36,6 +36,27 @@ struct bf_handle {
     int refine_force_c, refine_force_t, refine_force_variant;   // BF_REFINE_SHAPE="C,T[,variant]" in the environment: force the launch shape / kernel instantiation (tuning sweeps)
     int refine_concurrent;      // BF_OPT_REFINE_CONCURRENT
     int refine_timing;          // BF_REFINE_TIMING=1 in the environment: bf_refine's trace carries per-iteration phase cycle counts (diagnostic)
+    int frozen;                 // scratch may not grow any more: a captured CUDA graph (bf_engine) holds the pointers
+    int refine_force_persistent;   // BF_REFINE_PERSISTENT=G in the environment: stand-alone bf_refine launches G persistent clusters (the engine's shape; tests)
+};
+
+// A size that is either known on the host or read from device memory by the kernel itself (the graph-captured
+// engine step: kernel parameters never change, so every size that varies per keyframe lives in HBM).
+struct bf_dimref { int host; const int32_t* dev; };
+static inline bf_dimref bf_dim_host(int v) { bf_dimref d; d.host = v; d.dev = nullptr; return d; }
+static inline bf_dimref bf_dim_dev(const int32_t* p, int cap) { bf_dimref d; d.host = cap; d.dev = p; return d; }
+#ifdef __CUDACC__
+__device__ __forceinline__ int bf_dim(const bf_dimref d) { return d.dev ? *d.dev : d.host; }
+#endif
+
+// Every entry point runs on the handle's device whatever the caller's current device is (and restores it).
+struct bf_device_guard {
+    int prev;
+    bool switched;
+    explicit bf_device_guard(const bf_handle* h) : prev(-1), switched(false) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = (cudaSetDevice(h->device) == cudaSuccess);
+    }
+    ~bf_device_guard() { if (switched) cudaSetDevice(prev); }
 };
 
 static inline int bf_fail(bf_handle* h, int code, const char* what, const char* detail) {
@@ -60,6 +81,7 @@ static inline int bf_fail(bf_handle* h, int code, const char* what, const char* 
 static inline int bf_scratch(bf_handle* h, int slot, size_t bytes, void** out) {
     if (bytes < (4u << 20)) bytes = 4u << 20;           // 4 MB floor: maps of a few hundred boxes never regrow (a regrow is a device-wide sync)
     if (h->cap[slot] < bytes) {
+        if (h->frozen) return bf_fail(h, BF_ERR_CAPACITY, "bf_scratch", "scratch of a graph-captured engine cannot grow (raise the engine capacities)");
         if (h->buf[slot]) BF_CUDA(h, cudaFree(h->buf[slot]));
         h->buf[slot] = nullptr;
         h->cap[slot] = 0;

@@ -1,36 +1,117 @@
-// Device-resident map store: the per-keyframe state that demo.py keeps in Python
+// Device-resident fusion engine: the per-keyframe state that demo.py keeps in Python
 // containers (all_pred_box, per_frame_ins, BoxManager.fusion_list / fusion_flag / already_fusion) stays in HBM across
-// keyframes, so that a fusion step needs one H2D (the detections) and one 32-byte D2H.  The arithmetic is the same
-// as the reference-shaped entry points (bf_transform2world, bf_project_boxes, bf_nms3d, bf_corr2d, bf_refine); the
-// kernels here replace the host bookkeeping around them:
-//   bf_engine_ingest   demo.py:216-221, 243/248, 253-254   lift + project + append to map and per-frame store
-//   bf_engine_corr     instances.py:411-490, box_manager.py:90-129   small-object correspondence incl. its sequential tail
-//   bf_engine_compact  `all_pred_box[keep_idx]`, `box_manager.update(keep_idx)` (demo.py:292, 325-327)
-//   bf_engine_select   box_fusion.py:631-635   which map boxes get refined -> CSR for bf_refine
-//   bf_engine_apply    box_fusion.py:716-724   write fused rows, flags, already_fusion
-#include "bf_common.cuh"
+// keyframes and ONE call (bf_engine_step) runs a whole keyframe of demo.py:200-327.
+//
+// Design (round 2).  Nothing that varies per keyframe is a kernel parameter: the row counts, the detection count, the
+// intrinsics and poses live in device memory (bf_engine_state + the packed keyframe the step copies in), every kernel
+// reads them itself and runs on a fixed launch shape (grid-stride loops / persistent clusters).  The launch sequence is
+// therefore identical for every keyframe and is captured once per engine into three CUDA graphs:
+//   phase a  ingest (demo.py:216-221, 243/248, 253-254)  ->  corners -> score order -> planes -> pairs -> gate+counts
+//            -> greedy matching with record()              (Instances3D.spatial_association, demo.py:262)
+//   phase b  correspondence association incl. record_corr  (demo.py:273-289)
+//   phase c  all_pred_box[keep_idx] + box_manager.update (demo.py:292), check_valid_num (:297-298), selection of the
+//            boxes to fuse (box_fusion.py:631-635), bf_refine, write-back (:716-724), counters for the next keyframe.
+// bf_engine_step(.., phases = 7) replays all three back to back (three graph launches, no host decision in between);
+// the reference-shaped API replays them one by one because spatial_association / correspondence_association hand the
+// keep indices back to the caller.  The arithmetic is that of the stand-alone entries (same device functions).
+#include "bf_internal.cuh"
+#include "bf_record.cuh"
 
-// bf_map_buffers / bf_store_buffers / bf_fused_table: see include/boxfusion_b200.h
+struct bf_engine {
+    bf_handle* h;                     // private: its scratch is frozen once the graphs exist
+    bf_engine_cfg cfg;
+    bf_engine_buffers bufs;
+    // engine-owned device memory
+    float* in_dev;                    // packed keyframe (header + rows)
+    bf_engine_state* state;
+    int32_t *keep, *success, *todo, *offsets, *view_index, *order, *rank, *src, *snap, *upd, *its;
+    float *corners, *centers, *out;
+    double* boxes2d;
+    // host staging ring for the keyframe copy
+    enum { RING = 8 };
+    float* stage[RING];
+    cudaEvent_t stage_evt[RING];
+    int stage_next;
+    size_t in_floats;
+    // graphs
+    cudaStream_t cap_stream;
+    cudaGraphExec_t exec[8];          // one per phase bit + [7] the whole keyframe
+    int have_graph;
+    int launches[8];
+    char err[512];
+};
+
+static int e_fail(bf_engine* e, int code, const char* what, const char* detail) {
+    if (e) snprintf(e->err, sizeof(e->err), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+#define E_CUDA(e, expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) return e_fail((e), BF_ERR_CUDA, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// everything the engine kernels need, by value (kernel parameters never change -> graph replay)
+struct bf_engine_ctx {
+    bf_map_buffers map[2];
+    bf_store_buffers store;
+    int32_t* fflag;
+    bf_fused_table fused;
+    const float* in;
+    bf_engine_state* st;
+    int32_t *keep, *success, *todo, *offsets, *view_index, *src, *snap, *upd;
+    const float* out;
+    double* boxes2d;
+    int ncap, mcap, max_det;
+    float tgap, rgap, small_size, small_plus;
+    double small_threshold;
+    int check_valid, gap, use_fusion;
+};
 
 __device__ __forceinline__ float e_dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// ingest: one thread per detection.  in[] = packed keyframe: tensor_cam[n,6] R_cam[n,9] scores[n] box2d[n,4]
-// projxy[n,2] pose[16] pose_inv[16]  (pose_inv = torch.linalg.inv(pose), computed by the host like the reference)
-__global__ void bf_engine_ingest_kernel(const float* __restrict__ in, int n, float fx, float fy, float cx, float cy,
-                                        float W, float H, int frame_id, int box_count, int N, int M, int D,
-                                        bf_map_buffers mp, bf_store_buffers st, int32_t* __restrict__ fflag) {
+// phase a, kernel 1 - ingest: one thread per detection.  in[] = header (BF_KF_HEADER words) then tensor_cam[n,6] R_cam[n,9]
+// scores[n] box2d[n,4] projxy[n,2].  Appends rows [N, N+n) of the current map and [M, M+n) of the store; thread 0 derives the
+// keyframe's sizes for every later kernel.
+// sizes of the keyframe in flight, derived once by thread 0 of the ingest kernel for every later kernel
+__device__ __forceinline__ int e_begin_keyframe(const bf_engine_ctx& c, int i, int& N, int& M) {
+    bf_engine_state* st = c.st;
+    int n = __float_as_int(c.in[0]);
+    N = st->N; M = st->M;
+    bool fits = true;
+    if (n < 0 || n > c.max_det || N + n > c.ncap || M + n > c.mcap) { fits = false; n = 0; }
+    if (i == 0) {
+        if (!fits) st->status[4] = BF_ERR_CAPACITY;
+        st->n = n; st->Nall = N + n; st->first = (N == 0) ? 1 : 0;
+        st->Nnms = (N == 0) ? 0 : N + n;
+        st->any_new = 0; st->B = 0; st->SV = 0; st->maxV = 0;
+        st->Nnew = N + n;
+        st->pad[1] = 0;
+    }
+    return n;
+}
+
+__global__ void bf_engine_ingest_kernel(bf_engine_ctx c) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* in = c.in;
+    const int frame_id = __float_as_int(in[1]);
+    int N, M;
+    const int n = e_begin_keyframe(c, i, N, M);
     if (i >= n) return;
-    const float* tc = in + 6 * i;
-    const float* rc = in + 6 * n + 9 * i;
-    const float score = in[15 * n + i];
-    const float* b2 = in + 16 * n + 4 * i;
-    const float* pxy = in + 20 * n + 2 * i;
-    const float* pose = in + 22 * n;
-    const float* pinv = pose + 16;
+    const bf_map_buffers& mp = c.map[0];
+    const bf_store_buffers& sb = c.store;
+    const float fx = in[2], fy = in[3], cx = in[4], cy = in[5], W = in[6], H = in[7];
+    const float* pose = in + 8;
+    const float* pinv = in + 24;
+    const float* rows = in + BF_KF_HEADER;
+    const float* tc = rows + 6 * i;
+    const float* rc = rows + 6 * n + 9 * i;
+    const float score = rows[15 * n + i];
+    const float* b2 = rows + 16 * n + 4 * i;
+    const float* pxy = rows + 20 * n + 2 * i;
     float t[6], r[9];
     // boxes.py:825-833
 #pragma unroll
@@ -58,85 +139,81 @@ __global__ void bf_engine_ingest_kernel(const float* __restrict__ in, int n, flo
     }
     const size_t m = (size_t)N + i, s = (size_t)M + i;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { mp.tensor[6 * m + k] = t[k]; st.tensor[6 * s + k] = t[k]; }
+    for (int k = 0; k < 6; ++k) { mp.tensor[6 * m + k] = t[k]; sb.tensor[6 * s + k] = t[k]; }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { mp.R[9 * m + k] = r[k]; st.R[9 * s + k] = r[k]; }
+    for (int k = 0; k < 9; ++k) { mp.R[9 * m + k] = r[k]; sb.R[9 * s + k] = r[k]; }
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { mp.uv[16 * m + k] = uv[k]; st.uv[16 * s + k] = uv[k]; mp.pose[16 * m + k] = pose[k]; st.pose[16 * s + k] = pose[k]; }
-    mp.scores[m] = score; st.scores[s] = score;
+    for (int k = 0; k < 16; ++k) { mp.uv[16 * m + k] = uv[k]; sb.uv[16 * s + k] = uv[k]; mp.pose[16 * m + k] = pose[k]; sb.pose[16 * s + k] = pose[k]; }
+    mp.scores[m] = score; sb.scores[s] = score;
 #pragma unroll
     for (int k = 0; k < 4; ++k) mp.box2d[4 * m + k] = b2[k];
     mp.projxy[2 * m] = pxy[0]; mp.projxy[2 * m + 1] = pxy[1];
     mp.valid[m] = 0.f;
-    mp.init_id[m] = box_count + i;                        // demo.py:218
-    mp.frame_id[m] = frame_id;
+    mp.init_id[m] = M + i;                                // demo.py:218 (box_count = rows of the store)
+    mp.frame_id[m] = frame_id;                            // demo.py:217
     mp.fl[m * BF_FUSION_CAP] = M + i;                     // box_manager.py:24-28
     mp.flen[m] = 1;
-    fflag[D + i] = 0;
+    c.fflag[M + i] = 0;
+}
+
+// The same append for detections that were lifted and projected already (the reference-shaped API: the caller ran
+// transform2world / project_3d_boxes itself, demo.py:220-221): plain row copies from the caller's tensors.
+struct bf_world_rows { const float *tensor, *R, *scores, *box2d, *projxy, *uv; };
+__global__ void bf_engine_ingest_world_kernel(bf_engine_ctx c, bf_world_rows w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* in = c.in;
+    const int frame_id = __float_as_int(in[1]);
+    int N, M;
+    const int n = e_begin_keyframe(c, i, N, M);
+    if (i >= n) return;
+    const bf_map_buffers& mp = c.map[0];
+    const bf_store_buffers& sb = c.store;
+    const float* pose = in + 8;
+    const size_t m = (size_t)N + i, s = (size_t)M + i;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const float v = w.tensor[6 * (size_t)i + k]; mp.tensor[6 * m + k] = v; sb.tensor[6 * s + k] = v; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const float v = w.R[9 * (size_t)i + k]; mp.R[9 * m + k] = v; sb.R[9 * s + k] = v; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float v = w.uv[16 * (size_t)i + k];
+        mp.uv[16 * m + k] = v; sb.uv[16 * s + k] = v; mp.pose[16 * m + k] = pose[k]; sb.pose[16 * s + k] = pose[k];
+    }
+    const float score = w.scores[i];
+    mp.scores[m] = score; sb.scores[s] = score;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mp.box2d[4 * m + k] = w.box2d[4 * (size_t)i + k];
+    mp.projxy[2 * m] = w.projxy[2 * (size_t)i]; mp.projxy[2 * m + 1] = w.projxy[2 * (size_t)i + 1];
+    mp.valid[m] = 0.f;
+    mp.init_id[m] = M + i;
+    mp.frame_id[m] = frame_id;
+    mp.fl[m * BF_FUSION_CAP] = M + i;
+    mp.flen[m] = 1;
+    c.fflag[M + i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pose predicate of record_corr (box_manager.py:100-102): no centre term
-__device__ __forceinline__ bool e_views_differ(const float* __restrict__ p1, const float* __restrict__ p2, float tgap, float rgap) {
-    const float dx = p2[3] - p1[3], dy = p2[7] - p1[7], dz = p2[11] - p1[11];
-    const float baseline = sqrtf(dx * dx + dy * dy + dz * dz);
-    float tr = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) tr += p2[4 * r] * p1[4 * r] + p2[4 * r + 1] * p1[4 * r + 1] + p2[4 * r + 2] * p1[4 * r + 2];
-    const float c = fminf(fmaxf((tr - 1.f) * 0.5f, -1.f), 1.f);
-    const float angle = acosf(c) * 180.f / 3.14159265358979323846f;
-    return angle > rgap || baseline > tgap;
-}
-
-__device__ __forceinline__ void e_sorted_insert(int32_t* list, int& len, int32_t val) {
-    int k = len;
-    while (k > 0 && list[k - 1] > val) { list[k] = list[k - 1]; --k; }
-    list[k] = val;
-    ++len;
-}
-
-// BoxManager.record_corr(cur, [idx]) on keep FLAGS (box_manager.py:90-129)
-__device__ void e_record_corr(int cur, int idx, const bf_map_buffers& mp, const float* __restrict__ sposes,
-                              int32_t* __restrict__ fflag, int32_t* __restrict__ keep, float tgap, float rgap,
-                              int32_t* __restrict__ status) {
-    int32_t* lc = mp.fl + (size_t)cur * BF_FUSION_CAP;
-    const int32_t* li = mp.fl + (size_t)idx * BF_FUSION_CAP;
-    int len_c = mp.flen[cur];
-    const int len_i = mp.flen[idx];
-    if (len_i == 1) {
-        const float* pi = sposes + 16 * (size_t)mp.init_id[idx];
-        int cnt = 0;
-        for (int k = 0; k < len_c; ++k) cnt += e_views_differ(sposes + 16 * (size_t)lc[k], pi, tgap, rgap);
-        if (cnt == len_c && len_c < 5) {
-            if (len_c + 1 > BF_FUSION_CAP) status[0] = BF_ERR_CAPACITY; else e_sorted_insert(lc, len_c, mp.init_id[idx]);
-        }
-    } else {
-        const float* pc = sposes + 16 * (size_t)mp.init_id[cur];
-        int cnt = 0;
-        for (int k = 0; k < len_i; ++k) cnt += e_views_differ(sposes + 16 * (size_t)li[k], pc, tgap, rgap);
-        if (cnt == len_i && len_i < 5) {
-            if (len_c + len_i > BF_FUSION_CAP) status[0] = BF_ERR_CAPACITY;
-            else for (int k = 0; k < len_i; ++k) e_sorted_insert(lc, len_c, li[k]);
-        } else if (keep[cur]) { keep[cur] = 0; keep[idx] = 1; }          // keep[keep == cur_id] = idx
-        if (fflag[idx] == 1) fflag[cur] = 1;
-    }
-    mp.flen[cur] = len_c;
-}
-
-// correspondence_association (instances.py:411-490) for one keyframe, one CTA.
+// phase b - correspondence_association (instances.py:411-490) for one keyframe, one CTA; the sequential accept /
+// replace tail with BoxManager.record_corr (box_manager.py:90-129) runs on thread 0 through the shared bf_record_one.
 //   keep/success: flags over the N_glo + n boxes after nms_3d (keep is edited in place)
-//   pinv: np.linalg.inv(pose) of the current keyframe (float32, host)
-//   info[0] = 1 if any new box survived nms_3d (demo.py:269), else 0
+//   st->any_new = 1 if any new box survived nms_3d (demo.py:269)
+
 #define BF_ECORR_THREADS 256
 __global__ void __launch_bounds__(BF_ECORR_THREADS)
-bf_engine_corr_kernel(bf_map_buffers mp, const float* __restrict__ sposes, int32_t* __restrict__ fflag, int N_glo, int n,
-                      int32_t* __restrict__ keep, const int32_t* __restrict__ success,
-                      const float* __restrict__ pinv, double fx, double fy, double cx, double cy, double W, double H,
-                      float small_size, float small_plus, double threshold, float tgap, float rgap, double* __restrict__ boxes2d,
-                      int32_t* __restrict__ glo_keep_snapshot, int32_t* __restrict__ info, int32_t* __restrict__ status) {
+bf_engine_corr_kernel(bf_engine_ctx c) {
     __shared__ int s_any_new, s_any_small;
     __shared__ double s_bv[BF_ECORR_THREADS / 32];
     __shared__ int s_bi[BF_ECORR_THREADS / 32];
+    bf_engine_state* st = c.st;
+    if (st->first) return;
+    const bf_map_buffers& mp = c.map[0];
+    const int N_glo = st->N, n = st->n;
+    int32_t* keep = c.keep;
+    const int32_t* success = c.success;
+    const float* sposes = c.store.pose;
+    const float* in = c.in;
+    const double fx = (double)in[2], fy = (double)in[3], cx = (double)in[4], cy = (double)in[5], W = (double)in[6], H = (double)in[7];
+    const float* pinv = in + 40;                           // np.linalg.inv(pose), float32
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_any_new = 0; s_any_small = 0; }
     __syncthreads();
@@ -146,12 +223,16 @@ bf_engine_corr_kernel(bf_map_buffers mp, const float* __restrict__ sposes, int32
         if (keep[N_glo + j]) {
             s_any_new = 1;
             const float* d = mp.tensor + 6 * (size_t)(N_glo + j) + 3;
-            if (!(fmaxf(d[0], fmaxf(d[1], d[2])) > small_size) && !success[N_glo + j]) s_any_small = 1;
+            if (!(fmaxf(d[0], fmaxf(d[1], d[2])) > c.small_size) && !success[N_glo + j]) s_any_small = 1;
         }
     }
+    // membership in cur_keep_idx refers to the state right after nms_3d (:428-435): snapshot the new boxes' flags
+    for (int j = tid; j < n; j += T) c.snap[N_glo + j] = keep[N_glo + j];
     __syncthreads();
-    if (tid == 0) info[0] = s_any_new;
+    if (tid == 0) st->any_new = s_any_new;
     if (!s_any_new || !s_any_small || N_glo == 0) return;
+    double* boxes2d = c.boxes2d;
+    int32_t* glo_keep_snapshot = c.snap;
     // snapshot of the kept map boxes (global_keep_idx, :424) and their clipped 2-D boxes in the current view (:670-717)
     for (int g = tid; g < N_glo; g += T) {
         glo_keep_snapshot[g] = keep[g];
@@ -182,13 +263,15 @@ bf_engine_corr_kernel(bf_map_buffers mp, const float* __restrict__ sposes, int32
         boxes2d[4 * (size_t)g + 2] = ok ? umax : 0.0; boxes2d[4 * (size_t)g + 3] = ok ? vmax : 0.0;
     }
     __syncthreads();
+    bf_record_ctx rc;
+    rc.order = nullptr; rc.init_id = mp.init_id; rc.poses = sposes; rc.centers = nullptr; rc.fl = mp.fl; rc.flen = mp.flen;
+    rc.fflag = c.fflag; rc.keep = keep; rc.status = &st->status[1];
+    rc.translation_gap = c.tgap; rc.rotation_gap = c.rgap; rc.center_gap = 0.f;
     // small new boxes in index order; scoring in parallel, decision by thread 0 (:446-483)
     for (int j = 0; j < n; ++j) {
         const int cur_new = N_glo + j;
         const float* dn = mp.tensor + 6 * (size_t)cur_new + 3;
-        // membership in cur_keep_idx / cur_success_nms refers to the state right after nms_3d (:428-435): keep flags of
-        // NEW boxes are only cleared by this loop for the box itself or set back by a swap, so test the nms result
-        const bool cand = glo_keep_snapshot[N_glo + j] && !(fmaxf(dn[0], fmaxf(dn[1], dn[2])) > small_size) && !success[cur_new];
+        const bool cand = glo_keep_snapshot[N_glo + j] && !(fmaxf(dn[0], fmaxf(dn[1], dn[2])) > c.small_size) && !success[cur_new];
         if (!cand) continue;                                               // uniform: all threads read the same flags
         const float* a = mp.box2d + 4 * (size_t)cur_new;
         const double ax0 = a[0], ay0 = a[1], ax1 = a[2], ay1 = a[3];
@@ -203,7 +286,7 @@ bf_engine_corr_kernel(bf_map_buffers mp, const float* __restrict__ sposes, int32
             const double inter = iw * ih;
             double v = inter / (areaA + areaB - inter + 1e-6);
             const float* dg = mp.tensor + 6 * (size_t)g + 3;
-            v = v * ((fmaxf(dg[0], fmaxf(dg[1], dg[2])) < small_plus) ? 1.0 : 0.0);             // (:460-461)
+            v = v * ((fmaxf(dg[0], fmaxf(dg[1], dg[2])) < c.small_plus) ? 1.0 : 0.0);           // (:460-461)
             if (v > bv) { bv = v; bi = g; }
         }
 #pragma unroll
@@ -216,17 +299,18 @@ bf_engine_corr_kernel(bf_map_buffers mp, const float* __restrict__ sposes, int32
         __syncthreads();
         if (tid == 0) {
             for (int w = 1; w < T / 32; ++w) if (s_bv[w] > bv || (s_bv[w] == bv && s_bi[w] < bi)) { bv = s_bv[w]; bi = s_bi[w]; }
-            if (bi != 0x7fffffff && bv > threshold) {
+            if (bi != 0x7fffffff && bv > c.small_threshold) {
                 const int cidx = bi;
-                if (mp.scores[cidx] < mp.scores[cur_new]) {                // the new box wins (:471-477)
-                    keep[cidx] = 0;
-                    mp.valid[cur_new] += 1.f;
-                    e_record_corr(cur_new, cidx, mp, sposes, fflag, keep, tgap, rgap, status);
-                } else {                                                  // the old box wins (:478-483)
-                    keep[cur_new] = 0;
-                    mp.valid[cidx] += 1.f;
-                    e_record_corr(cidx, cur_new, mp, sposes, fflag, keep, tgap, rgap, status);
+                int cur, idx;
+                if (mp.scores[cidx] < mp.scores[cur_new]) { cur = cur_new; idx = cidx; }   // the new box wins (:471-477)
+                else { cur = cidx; idx = cur_new; }                                        // the old box wins (:478-483)
+                keep[idx] = 0;                                                             // keep_idx = keep_idx[keep_idx != idx]
+                mp.valid[cur] += 1.f;
+                int len_c = mp.flen[cur];
+                if (bf_record_one(rc, cur, idx, mp.fl + (size_t)cur * BF_FUSION_CAP, len_c) && keep[cur]) {
+                    keep[cur] = 0; keep[idx] = 1;                                          // keep[keep == cur_id] = idx (box_manager.py:124)
                 }
+                mp.flen[cur] = len_c;
             }
         }
         __syncthreads();
@@ -234,18 +318,31 @@ bf_engine_corr_kernel(bf_map_buffers mp, const float* __restrict__ sposes, int32
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// compaction: one CTA scans the keep flags -> src[] (old index of every new row) and info[1] = N_new;
-// a second kernel gathers every field.
+// phase c - compaction: one CTA scans the keep flags -> src[] (old index of every new row), st->Nnew, and flips the current
+// map buffer set; a second kernel gathers every field.  `stale` != 0: the flags are formed here from
+// BoxManager.check_valid_num's rule (box_manager.py:151-166) over the already compacted map.
 #define BF_ESCAN_THREADS 1024
 __global__ void __launch_bounds__(BF_ESCAN_THREADS)
-bf_engine_scan_kernel(const int32_t* __restrict__ keep, int N, int32_t* __restrict__ src, int32_t* __restrict__ info) {
+bf_engine_scan_kernel(bf_engine_ctx c, int stale) {
     __shared__ int s_w[BF_ESCAN_THREADS / 32];
     __shared__ int s_total;
+    bf_engine_state* st = c.st;
+    // first keyframe: every detection becomes a map row as is; check_valid_num only runs when a new box survived (demo.py:269, 297)
+    if (st->first || (stale && !st->any_new)) { if (threadIdx.x == 0) st->pad[1] = 0; return; }
+    const bf_map_buffers& mp = c.map[0];
+    const int frame_id = __float_as_int(c.in[1]);
+    const int N = stale ? st->Nnew : st->Nall;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (N + BF_ESCAN_THREADS - 1) / BF_ESCAN_THREADS;
-    const int lo = tid * per, hi = min(N, lo + per);
+    const int lo = min(N, tid * per), hi = min(N, lo + per);
+    const int thr = frame_id - c.gap;
     int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += keep[i] ? 1 : 0;
+    for (int i = lo; i < hi; ++i) {
+        int k;
+        if (stale) { k = !((mp.valid[i] == 0.f) && (mp.frame_id[i] < thr)); c.keep[i] = k; }
+        else k = c.keep[i] ? 1 : 0;
+        cnt += k;
+    }
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -260,26 +357,32 @@ bf_engine_scan_kernel(const int32_t* __restrict__ keep, int N, int32_t* __restri
     }
     __syncthreads();
     int pos = incl - cnt + (warp ? s_w[warp - 1] : 0);
-    for (int i = lo; i < hi; ++i) if (keep[i]) src[pos++] = i;
-    if (tid == 0) info[1] = s_total;
+    for (int i = lo; i < hi; ++i) if (c.keep[i]) c.src[pos++] = i;
+    __syncthreads();
+    if (tid == 0) { st->Nnew = s_total; st->pad[1] = 1; }    // rows to gather; a gather is pending
 }
 
-__global__ void bf_engine_gather_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ info, bf_map_buffers a,
-                                        bf_map_buffers b) {
-    const int n_new = info[1];
-    const int k = blockIdx.x;                        // new row
-    if (k >= n_new) return;
-    const size_t s = (size_t)src[k], d = (size_t)k;
+// gather the kept rows of map[0] into map[1] (dir = 0), then copy them back to map[0] (dir = 1): map[0] is always the
+// current buffer set, so the stand-alone kernels (corners, score order, NMS) can take its plain pointers.
+__global__ void bf_engine_gather_kernel(bf_engine_ctx c, int dir) {
+    bf_engine_state* st = c.st;
+    if (!st->pad[1]) return;
+    const int n_new = st->Nnew;
+    const bf_map_buffers& a = c.map[dir ? 1 : 0];
+    const bf_map_buffers& b = c.map[dir ? 0 : 1];
     const int t = threadIdx.x;                       // 64 threads: field elements
-    if (t < 6) b.tensor[6 * d + t] = a.tensor[6 * s + t];
-    if (t < 9) b.R[9 * d + t] = a.R[9 * s + t];
-    if (t < 16) { b.pose[16 * d + t] = a.pose[16 * s + t]; b.uv[16 * d + t] = a.uv[16 * s + t]; }
-    if (t < 4) b.box2d[4 * d + t] = a.box2d[4 * s + t];
-    if (t < 2) b.projxy[2 * d + t] = a.projxy[2 * s + t];
-    if (t < BF_FUSION_CAP) b.fl[d * BF_FUSION_CAP + t] = a.fl[s * BF_FUSION_CAP + t];
-    if (t == 0) {
-        b.scores[d] = a.scores[s]; b.valid[d] = a.valid[s]; b.init_id[d] = a.init_id[s]; b.frame_id[d] = a.frame_id[s];
-        b.flen[d] = a.flen[s];
+    for (int k = blockIdx.x; k < n_new; k += gridDim.x) {
+        const size_t s = dir ? (size_t)k : (size_t)c.src[k], d = (size_t)k;
+        if (t < 6) b.tensor[6 * d + t] = a.tensor[6 * s + t];
+        if (t < 9) b.R[9 * d + t] = a.R[9 * s + t];
+        if (t < 16) { b.pose[16 * d + t] = a.pose[16 * s + t]; b.uv[16 * d + t] = a.uv[16 * s + t]; }
+        if (t < 4) b.box2d[4 * d + t] = a.box2d[4 * s + t];
+        if (t < 2) b.projxy[2 * d + t] = a.projxy[2 * s + t];
+        if (t < BF_FUSION_CAP) b.fl[d * BF_FUSION_CAP + t] = a.fl[s * BF_FUSION_CAP + t];
+        if (t == 0) {
+            b.scores[d] = a.scores[s]; b.valid[d] = a.valid[s]; b.init_id[d] = a.init_id[s]; b.frame_id[d] = a.frame_id[s];
+            b.flen[d] = a.flen[s];
+        }
     }
 }
 
@@ -302,20 +405,22 @@ __device__ __forceinline__ bool e_in_fused(const bf_fused_table& ft, int F, cons
 }
 
 // which map boxes are refined this keyframe (box_fusion.py:631-635) -> todo[], CSR offsets / view_index;
-// info[2] = B, info[3] = sum V, info[4] = max V.  One CTA.
+// st->B, st->SV, st->maxV.  One CTA.
 __global__ void __launch_bounds__(BF_ESCAN_THREADS)
-bf_engine_select_kernel(bf_map_buffers mp, bf_fused_table ft, int32_t* __restrict__ info, int32_t* __restrict__ todo,
-                        int32_t* __restrict__ offsets, int32_t* __restrict__ view_index, int max_views) {
+bf_engine_select_kernel(bf_engine_ctx c) {
     __shared__ int s_w[BF_ESCAN_THREADS / 32];
     __shared__ int s_wv[BF_ESCAN_THREADS / 32];
     __shared__ int s_maxv;
+    bf_engine_state* st = c.st;
+    const bf_map_buffers& mp = c.map[0];
+    const bf_fused_table& ft = c.fused;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = info[1], F = ft.count[0];
-    const bool active = info[0] != 0;                         // demo.py:269: fusion only when a new box survived
+    const int N = st->Nnew, F = ft.count[0];
+    const bool active = st->any_new != 0 && !st->first && c.use_fusion;   // demo.py:269: fusion only when a new box survived
     if (tid == 0) s_maxv = 0;
     __syncthreads();
     const int per = (N + BF_ESCAN_THREADS - 1) / BF_ESCAN_THREADS;
-    const int lo = tid * per, hi = min(N, lo + per);
+    const int lo = min(N, tid * per), hi = min(N, lo + per);
     int cnt = 0, vsum = 0, vmax = 0;
     unsigned long long picks = 0ull;                          // per <= 64 rows per thread (N <= 65536)
     for (int i = lo; i < hi && active; ++i) {
@@ -323,6 +428,7 @@ bf_engine_select_kernel(bf_map_buffers mp, bf_fused_table ft, int32_t* __restric
         if (len < 3) continue;
         const int32_t* l = mp.fl + (size_t)i * BF_FUSION_CAP;
         if (e_in_fused(ft, F, l, len, e_list_hash(l, len))) continue;
+        if (len > BF_MAX_VIEWS) { st->status[5] = BF_ERR_CAPACITY; continue; }
         if (i - lo < 64) picks |= 1ull << (i - lo);
         ++cnt; vsum += len; vmax = max(vmax, len);
     }
@@ -350,104 +456,383 @@ bf_engine_select_kernel(bf_map_buffers mp, bf_fused_table ft, int32_t* __restric
     for (int i = lo; i < hi; ++i) {
         if (!((picks >> (i - lo)) & 1ull)) continue;
         const int len = mp.flen[i];
-        todo[pos] = i; offsets[pos] = vpos;
-        for (int k = 0; k < len; ++k) view_index[vpos + k] = mp.fl[(size_t)i * BF_FUSION_CAP + k];
+        c.todo[pos] = i; c.offsets[pos] = vpos;
+        for (int k = 0; k < len; ++k) c.view_index[vpos + k] = mp.fl[(size_t)i * BF_FUSION_CAP + k];
         ++pos; vpos += len;
     }
     if (tid == BF_ESCAN_THREADS - 1) {
         const int B = s_w[BF_ESCAN_THREADS / 32 - 1], SV = s_wv[BF_ESCAN_THREADS / 32 - 1];
-        offsets[B] = SV;
-        info[2] = B; info[3] = SV; info[4] = s_maxv;
-        if (s_maxv > max_views) info[5] = BF_ERR_CAPACITY;
+        c.offsets[B] = SV;
+        st->B = B; st->SV = SV; st->maxV = s_maxv;
+        st->refine_boxes_total += B; st->refine_views_total += SV;
     }
 }
 
 // write back fused boxes (box_fusion.py:716-724), sequentially in map order like the reference's loop
-__global__ void bf_engine_apply_kernel(bf_map_buffers mp, bf_fused_table ft, int32_t* __restrict__ fflag,
-                                       const int32_t* __restrict__ info, const int32_t* __restrict__ todo,
-                                       const float* __restrict__ out, const int32_t* __restrict__ upd, int32_t* __restrict__ status) {
+__global__ void bf_engine_apply_kernel(bf_engine_ctx c) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int B = info[2];
+    bf_engine_state* st = c.st;
+    const bf_map_buffers& mp = c.map[0];
+    const bf_fused_table& ft = c.fused;
+    const int B = st->B;
     int F = ft.count[0];
     for (int k = 0; k < B; ++k) {
-        const int i = todo[k];
+        const int i = c.todo[k];
         const int len = mp.flen[i];
         const int32_t* l = mp.fl + (size_t)i * BF_FUSION_CAP;
         const unsigned long long h = e_list_hash(l, len);
         if (e_in_fused(ft, F, l, len, h)) continue;           // fused earlier in this very call (check_if_fusion, :634)
-        if (!upd[k]) continue;
-        for (int c = 0; c < 6; ++c) mp.tensor[6 * (size_t)i + c] = out[6 * (size_t)k + c];
-        fflag[i] = 1;
-        if (F >= ft.cap) { status[0] = BF_ERR_CAPACITY; continue; }
-        for (int c = 0; c < len; ++c) ft.lists[(size_t)F * BF_FUSION_CAP + c] = l[c];
+        if (!c.upd[k]) continue;
+        for (int q = 0; q < 6; ++q) mp.tensor[6 * (size_t)i + q] = c.out[6 * (size_t)k + q];
+        c.fflag[i] = 1;
+        if (F >= ft.cap) { st->status[3] = BF_ERR_CAPACITY; continue; }
+        for (int q = 0; q < len; ++q) ft.lists[(size_t)F * BF_FUSION_CAP + q] = l[q];
         ft.len[F] = len; ft.hash[F] = h;
         ++F;
     }
     ft.count[0] = F;
 }
 
+// close the keyframe: the counters the next keyframe starts from
+__global__ void bf_engine_finish_kernel(bf_engine_ctx c) {
+    bf_engine_state* st = c.st;
+    st->N = st->Nnew;
+    st->M = st->M + st->n;
+    st->steps += 1;
+    st->n = 0;
+}
+
+// copies the IoU stage's overflow flag into the sticky status (the work list is fixed-size inside a graph)
+__global__ void bf_engine_nms_status_kernel(bf_engine_ctx c, const unsigned long long* __restrict__ counters) {
+    if (counters[5]) c.st->status[6] = BF_ERR_CAPACITY;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int bf_engine_ingest(bf_handle* h, const float* packed, int n, float fx, float fy, float cx, float cy, float W,
-                                float H, int frame_id, int box_count, int N, int M, int D, const bf_map_buffers* mp,
-                                const bf_store_buffers* st, int32_t* fflag, void* stream) {
-    if (!h || !packed || !mp || !st || !fflag || n < 0) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_engine_ingest", "bad argument");
-    if (n == 0) return BF_OK;
-    bf_engine_ingest_kernel<<<bf_blocks(n, 64), 64, 0, (cudaStream_t)stream>>>(packed, n, fx, fy, cx, cy, W, H, frame_id,
-                                                                           box_count, N, M, D, *mp, *st, fflag);
-    BF_LAUNCH_CHECK(h, "bf_engine_ingest_kernel");
+static bf_engine_ctx e_ctx(const bf_engine* e) {
+    bf_engine_ctx c;
+    c.map[0] = e->bufs.map[0]; c.map[1] = e->bufs.map[1]; c.store = e->bufs.store; c.fflag = e->bufs.fusion_flag; c.fused = e->bufs.fused;
+    c.in = e->in_dev; c.st = e->state;
+    c.keep = e->keep; c.success = e->success; c.todo = e->todo; c.offsets = e->offsets; c.view_index = e->view_index;
+    c.src = e->src; c.snap = e->snap; c.upd = e->upd; c.out = e->out; c.boxes2d = e->boxes2d;
+    c.ncap = e->cfg.map_capacity; c.mcap = e->cfg.store_capacity; c.max_det = e->cfg.max_det;
+    c.tgap = e->cfg.translation_gap; c.rgap = e->cfg.rotation_gap; c.small_size = e->cfg.small_size; c.small_plus = e->cfg.small_plus;
+    c.small_threshold = e->cfg.small_threshold; c.check_valid = e->cfg.check_valid; c.gap = e->cfg.gap; c.use_fusion = e->cfg.use_fusion;
+    return c;
+}
+
+#define E_LAUNCH_CHECK(e, name)                                                               \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) return e_fail((e), BF_ERR_CUDA, name, cudaGetErrorString(e__)); \
+    } while (0)
+#define E_SUB(e, expr)                                                                        \
+    do {                                                                                      \
+        int rc__ = (expr);                                                                    \
+        if (rc__) { snprintf((e)->err, sizeof((e)->err), "%s", (e)->h->err); return rc__; }   \
+    } while (0)
+
+// ---- the launch sequences (issued eagerly or under stream capture); each returns the number of kernels it launches ----
+// phase bits of bf_engine_step (include/boxfusion_b200.h)
+enum { PH_INGEST = 0, PH_NMS, PH_CORR, PH_COMPACT, PH_VALID, PH_FUSE, PH_FINISH, PH_COUNT };
+
+static int e_ph_ingest(bf_engine* e, cudaStream_t st, int* L) {
+    const bf_engine_ctx c = e_ctx(e);
+    bf_engine_ingest_kernel<<<bf_blocks(e->cfg.max_det, 64), 64, 0, st>>>(c);
+    E_LAUNCH_CHECK(e, "bf_engine_ingest_kernel");
+    *L = 1;
     return BF_OK;
 }
 
-extern "C" int bf_engine_corr(bf_handle* h, const bf_map_buffers* mp, const float* store_poses, int32_t* fflag, int N_glo,
-                              int n, int32_t* keep, const int32_t* success, const float* pose_inv_np, float fx, float fy,
-                              float cx, float cy, float W, float H, float small_size, float small_plus, double threshold,
-                              float translation_gap, float rotation_gap, int32_t* info, int32_t* status, void* stream) {
-    if (!h || !mp || !keep || !success || !info || !status || N_glo < 0 || n < 0)
-        return bf_fail(h, BF_ERR_INVALID_ARG, "bf_engine_corr", "bad argument");
-    void* p;
-    int rc = bf_scratch(h, BF_SCRATCH_MISC, sizeof(double) * 4 * (size_t)(N_glo + 1) + sizeof(int32_t) * (size_t)(N_glo + n + 1), &p);
-    if (rc) return rc;
-    double* boxes2d = (double*)p;
-    int32_t* snap = (int32_t*)(boxes2d + 4 * (size_t)(N_glo + 1));
-    // the snapshot also covers the new boxes' keep flags as nms_3d left them
-    BF_CUDA(h, cudaMemcpyAsync(snap + N_glo, keep + N_glo, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    bf_engine_corr_kernel<<<1, BF_ECORR_THREADS, 0, (cudaStream_t)stream>>>(*mp, store_poses, fflag, N_glo, n, keep, success,
-                                                                          pose_inv_np, (double)fx, (double)fy, (double)cx,
-                                                                          (double)cy, (double)W, (double)H, small_size, small_plus,
-                                                                          threshold, translation_gap, rotation_gap, boxes2d, snap,
-                                                                          info, status);
-    BF_LAUNCH_CHECK(h, "bf_engine_corr_kernel");
+// Instances3D.spatial_association (demo.py:262): corners / centres of the Nall rows, score order, NMS with record()
+static int e_ph_nms(bf_engine* e, cudaStream_t st, int* L) {
+    const bf_engine_ctx c = e_ctx(e);
+    const bf_engine_cfg& g = e->cfg;
+    const bf_map_buffers& mp = e->bufs.map[0];
+    bf_handle* h = e->h;
+    const bf_dimref Nd = bf_dim_dev(&e->state->Nnms, g.map_capacity);
+    E_SUB(e, bf_box_corners_run(h, mp.tensor, mp.R, Nd, e->corners, e->centers, st));
+    E_SUB(e, bf_score_order_run(h, mp.scores, Nd, e->order, e->rank, st));
+    E_SUB(e, bf_nms3d_run(h, e->corners, e->centers, Nd, e->order, e->rank, mp.init_id, e->bufs.store.pose, mp.fl, mp.flen,
+                          e->bufs.fusion_flag, g.nms_threshold, g.translation_gap, g.rotation_gap, g.center_gap, g.iou_mode,
+                          e->keep, e->success, &e->state->status[0], st));
+    bf_engine_nms_status_kernel<<<1, 1, 0, st>>>(c, (const unsigned long long*)h->buf[BF_SCRATCH_COUNTERS]);
+    E_LAUNCH_CHECK(e, "bf_engine_nms_status_kernel");
+    // corners, order, planes, pairs, count, greedy (sparse), greedy (dense, if the map is small enough), status
+    *L = 7 + (g.map_capacity <= 16384 ? 1 : 0);
     return BF_OK;
 }
 
-extern "C" int bf_engine_compact(bf_handle* h, const int32_t* keep, int N, const bf_map_buffers* from, const bf_map_buffers* to,
-                                 int32_t* info, void* stream) {
-    if (!h || !keep || !from || !to || !info || N < 0 || N > 65536) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_engine_compact", "bad argument");
-    void* p;
-    int rc = bf_scratch(h, BF_SCRATCH_RANK, sizeof(int32_t) * (size_t)(N + 1), &p);
+static int e_ph_corr(bf_engine* e, cudaStream_t st, int* L) {
+    const bf_engine_ctx c = e_ctx(e);
+    bf_engine_corr_kernel<<<1, BF_ECORR_THREADS, 0, st>>>(c);
+    E_LAUNCH_CHECK(e, "bf_engine_corr_kernel");
+    *L = 1;
+    return BF_OK;
+}
+
+static int e_compaction(bf_engine* e, cudaStream_t st, int stale, int* L) {
+    const bf_engine_ctx c = e_ctx(e);
+    const int ggrid = e->cfg.map_capacity < 1024 ? e->cfg.map_capacity : 1024;
+    bf_engine_scan_kernel<<<1, BF_ESCAN_THREADS, 0, st>>>(c, stale);
+    E_LAUNCH_CHECK(e, "bf_engine_scan_kernel");
+    bf_engine_gather_kernel<<<ggrid, 64, 0, st>>>(c, 0);
+    E_LAUNCH_CHECK(e, "bf_engine_gather_kernel");
+    bf_engine_gather_kernel<<<ggrid, 64, 0, st>>>(c, 1);
+    E_LAUNCH_CHECK(e, "bf_engine_gather_kernel");
+    *L = 3;
+    return BF_OK;
+}
+// all_pred_box[keep_idx] + box_manager.update(keep_idx) (demo.py:292 / 325-327)
+static int e_ph_compact(bf_engine* e, cudaStream_t st, int* L) { return e_compaction(e, st, 0, L); }
+// BoxManager.check_valid_num (box_manager.py:151-166, demo.py:297-298)
+static int e_ph_valid(bf_engine* e, cudaStream_t st, int* L) { return e_compaction(e, st, 1, L); }
+
+// BoxFusion.boxfusion (demo.py:304-305): selection, refinement, write-back
+static int e_ph_fuse(bf_engine* e, cudaStream_t st, int* L) {
+    const bf_engine_ctx c = e_ctx(e);
+    const bf_engine_cfg& g = e->cfg;
+    bf_engine_select_kernel<<<1, BF_ESCAN_THREADS, 0, st>>>(c);
+    E_LAUNCH_CHECK(e, "bf_engine_select_kernel");
+    bf_refine_cfg rc = g.refine;
+    rc.views_total = 0; rc.max_views = 0;
+    bf_refine_dev_args dv;
+    dv.B_dev = &e->state->B; dv.intr_dev = e->in_dev + 2; dv.max_boxes = g.map_capacity;
+    const bf_store_buffers& sb = e->bufs.store;
+    E_SUB(e, bf_refine_run(e->h, g.pst, g.P, sb.tensor, sb.R, sb.scores, sb.uv, sb.pose, e->offsets, e->view_index,
+                           g.map_capacity, &rc, e->out, e->upd, e->its, nullptr, &e->state->status[2], &dv, st));
+    bf_engine_apply_kernel<<<1, 32, 0, st>>>(c);
+    E_LAUNCH_CHECK(e, "bf_engine_apply_kernel");
+    *L = 3;
+    return BF_OK;
+}
+
+static int e_ph_finish(bf_engine* e, cudaStream_t st, int* L) {
+    const bf_engine_ctx c = e_ctx(e);
+    bf_engine_finish_kernel<<<1, 1, 0, st>>>(c);
+    E_LAUNCH_CHECK(e, "bf_engine_finish_kernel");
+    *L = 1;
+    return BF_OK;
+}
+
+typedef int (*e_phase_fn)(bf_engine*, cudaStream_t, int*);
+static const e_phase_fn e_phases[PH_COUNT] = {e_ph_ingest, e_ph_nms, e_ph_corr, e_ph_compact, e_ph_valid, e_ph_fuse, e_ph_finish};
+
+static int e_issue(bf_engine* e, int phases, cudaStream_t st, int* launches) {
+    int total = 0;
+    for (int p = 0; p < PH_COUNT; ++p) {
+        if (!(phases & (1 << p))) continue;
+        int L = 0;
+        const int rc = e_phases[p](e, st, &L);
+        if (rc) return rc;
+        total += L;
+    }
+    if (launches) *launches = total;
+    return BF_OK;
+}
+
+static int e_capture_one(bf_engine* e, int phases, cudaGraphExec_t* exec, int* launches) {
+    cudaGraph_t graph = nullptr;
+    E_CUDA(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = e_issue(e, phases, e->cap_stream, launches);
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return e_fail(e, BF_ERR_CUDA, "cudaStreamEndCapture", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return e_fail(e, BF_ERR_CUDA, "cudaGraphInstantiate", cudaGetErrorString(ie));
+    return BF_OK;
+}
+
+// the whole keyframe as the engine's own configuration runs it
+static int e_full_mask(const bf_engine* e) {
+    return (1 << PH_INGEST) | (1 << PH_NMS) | (1 << PH_CORR) | (1 << PH_COMPACT) | (e->cfg.check_valid ? (1 << PH_VALID) : 0) |
+           (e->cfg.use_fusion ? (1 << PH_FUSE) : 0) | (1 << PH_FINISH);
+}
+
+extern "C" const char* bf_engine_last_error(bf_engine* e) { return e ? e->err : "null engine"; }
+
+extern "C" void bf_engine_destroy(bf_engine* e) {
+    if (!e) return;
+    if (e->h) cudaSetDevice(e->h->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < PH_COUNT + 1; ++p) if (e->exec[p]) cudaGraphExecDestroy(e->exec[p]);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    for (int i = 0; i < bf_engine::RING; ++i) { if (e->stage[i]) cudaFreeHost(e->stage[i]); if (e->stage_evt[i]) cudaEventDestroy(e->stage_evt[i]); }
+    void* bufs[] = {e->in_dev, e->state, e->keep, e->success, e->todo, e->offsets, e->view_index, e->order, e->rank, e->src, e->snap,
+                    e->upd, e->its, e->corners, e->centers, e->out, e->boxes2d};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (e->h) bf_destroy(e->h);
+    free(e);
+}
+
+extern "C" int bf_engine_create(int device, const bf_engine_cfg* cfg, const bf_engine_buffers* bufs, bf_engine** out) {
+    if (!out) return BF_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!cfg || !bufs || cfg->map_capacity < 1 || cfg->map_capacity > 65536 || cfg->store_capacity < 1 || cfg->max_det < 1 ||
+        cfg->max_det > cfg->map_capacity || !cfg->pst || cfg->P < 1 || cfg->P > BF_MAX_PARTICLES || cfg->refine.iters < 1 ||
+        cfg->refine.max_hits < 1 || cfg->refine.max_hits > 4096)
+        return BF_ERR_INVALID_ARG;
+    bf_engine* e = (bf_engine*)calloc(1, sizeof(bf_engine));
+    if (!e) return BF_ERR_INVALID_ARG;
+    int rc = bf_create(device, &e->h);
+    if (rc) { free(e); return rc; }
+    bf_device_guard guard(e->h);
+    e->cfg = *cfg; e->bufs = *bufs;
+    const size_t ncap = (size_t)cfg->map_capacity;
+    e->in_floats = BF_KF_HEADER + (size_t)BF_KF_ROW * cfg->max_det;
+#define E_ALLOC(ptr, bytes) do { cudaError_t ce = cudaMalloc((void**)&(ptr), (bytes)); if (ce != cudaSuccess) { bf_engine_destroy(e); return BF_ERR_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
+    E_ALLOC(e->in_dev, sizeof(float) * e->in_floats);
+    E_ALLOC(e->state, sizeof(bf_engine_state));
+    E_ALLOC(e->keep, sizeof(int32_t) * ncap); E_ALLOC(e->success, sizeof(int32_t) * ncap); E_ALLOC(e->todo, sizeof(int32_t) * ncap);
+    E_ALLOC(e->offsets, sizeof(int32_t) * (ncap + 1)); E_ALLOC(e->view_index, sizeof(int32_t) * ncap * BF_FUSION_CAP);
+    E_ALLOC(e->order, sizeof(int32_t) * ncap); E_ALLOC(e->rank, sizeof(int32_t) * ncap); E_ALLOC(e->src, sizeof(int32_t) * (ncap + 1));
+    E_ALLOC(e->snap, sizeof(int32_t) * (ncap + 1)); E_ALLOC(e->upd, sizeof(int32_t) * ncap); E_ALLOC(e->its, sizeof(int32_t) * ncap);
+    E_ALLOC(e->corners, sizeof(float) * 24 * ncap); E_ALLOC(e->centers, sizeof(float) * 3 * ncap); E_ALLOC(e->out, sizeof(float) * 6 * ncap);
+    E_ALLOC(e->boxes2d, sizeof(double) * 4 * (ncap + 1));
+#undef E_ALLOC
+    for (int i = 0; i < bf_engine::RING; ++i) {
+        if (cudaMallocHost((void**)&e->stage[i], sizeof(float) * e->in_floats) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->stage_evt[i], cudaEventDisableTiming) != cudaSuccess) { bf_engine_destroy(e); return BF_ERR_CUDA; }
+    }
+    if (cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { bf_engine_destroy(e); return BF_ERR_CUDA; }
+    *out = e;                                             // from here on the caller reads bf_engine_last_error and destroys on failure
+    // one eager pass over an empty keyframe: allocates every scratch block at its bound and validates the launches
+    rc = e_issue(e, (1 << PH_COUNT) - 1, e->cap_stream, nullptr);
     if (rc) return rc;
-    bf_engine_scan_kernel<<<1, BF_ESCAN_THREADS, 0, (cudaStream_t)stream>>>(keep, N, (int32_t*)p, info);
-    BF_LAUNCH_CHECK(h, "bf_engine_scan_kernel");
-    if (N > 0) {
-        bf_engine_gather_kernel<<<N, 64, 0, (cudaStream_t)stream>>>((const int32_t*)p, info, *from, *to);
-        BF_LAUNCH_CHECK(h, "bf_engine_gather_kernel");
+    if (cudaStreamSynchronize(e->cap_stream) != cudaSuccess) return e_fail(e, BF_ERR_CUDA, "bf_engine_create", cudaGetErrorString(cudaGetLastError()));
+    cudaMemset(e->state, 0, sizeof(bf_engine_state));
+    e->h->frozen = 1;
+    if (cfg->use_graph) {
+        for (int p = 0; p < PH_COUNT; ++p)
+            if ((rc = e_capture_one(e, 1 << p, &e->exec[p], &e->launches[p]))) return rc;
+        if ((rc = e_capture_one(e, e_full_mask(e), &e->exec[PH_COUNT], &e->launches[PH_COUNT]))) return rc;
+        e->have_graph = 1;
+    } else {
+        // launch counts of the eager sequences (same kernels)
+        e->launches[PH_INGEST] = 1; e->launches[PH_NMS] = 7 + (cfg->map_capacity <= 16384 ? 1 : 0); e->launches[PH_CORR] = 1;
+        e->launches[PH_COMPACT] = 3; e->launches[PH_VALID] = 3; e->launches[PH_FUSE] = 3; e->launches[PH_FINISH] = 1;
+        int tot = 0;
+        for (int p = 0; p < PH_COUNT; ++p) if (e_full_mask(e) & (1 << p)) tot += e->launches[p];
+        e->launches[PH_COUNT] = tot;
     }
     return BF_OK;
 }
 
-extern "C" int bf_engine_select(bf_handle* h, const bf_map_buffers* mp, const bf_fused_table* ft, int32_t* info, int32_t* todo,
-                                int32_t* offsets, int32_t* view_index, void* stream) {
-    if (!h || !mp || !ft || !info || !todo || !offsets || !view_index) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_engine_select", "bad argument");
-    bf_engine_select_kernel<<<1, BF_ESCAN_THREADS, 0, (cudaStream_t)stream>>>(*mp, *ft, info, todo, offsets, view_index, BF_MAX_VIEWS);
-    BF_LAUNCH_CHECK(h, "bf_engine_select_kernel");
+extern "C" int bf_engine_reset(bf_engine* e, void* stream) {
+    if (!e) return BF_ERR_INVALID_ARG;
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    E_CUDA(e, cudaMemsetAsync(e->state, 0, sizeof(bf_engine_state), st));
+    E_CUDA(e, cudaMemsetAsync(e->bufs.fused.count, 0, sizeof(int32_t), st));
     return BF_OK;
 }
 
-extern "C" int bf_engine_apply(bf_handle* h, const bf_map_buffers* mp, const bf_fused_table* ft, int32_t* fflag,
-                               const int32_t* info, const int32_t* todo, const float* out, const int32_t* upd, int32_t* status,
-                               void* stream) {
-    if (!h || !mp || !ft || !fflag || !info || !todo || !out || !upd || !status) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_engine_apply", "bad argument");
-    bf_engine_apply_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*mp, *ft, fflag, info, todo, out, upd, status);
-    BF_LAUNCH_CHECK(h, "bf_engine_apply_kernel");
+static int e_run(bf_engine* e, int phases, cudaStream_t st) {
+    if (!e->have_graph) return e_issue(e, phases, st, nullptr);
+    if (phases == e_full_mask(e)) { E_CUDA(e, cudaGraphLaunch(e->exec[PH_COUNT], st)); return BF_OK; }
+    for (int p = 0; p < PH_COUNT; ++p)
+        if (phases & (1 << p)) E_CUDA(e, cudaGraphLaunch(e->exec[p], st));
+    return BF_OK;
+}
+
+// host -> device copy of `floats` words into in_dev through the pinned staging ring
+static int e_upload(bf_engine* e, const float* src, size_t floats, cudaStream_t st) {
+    const int slot = e->stage_next;
+    e->stage_next = (slot + 1) % bf_engine::RING;
+    E_CUDA(e, cudaEventSynchronize(e->stage_evt[slot]));       // the copy issued RING keyframes ago has left this slot
+    memcpy(e->stage[slot], src, sizeof(float) * floats);
+    E_CUDA(e, cudaMemcpyAsync(e->in_dev, e->stage[slot], sizeof(float) * floats, cudaMemcpyHostToDevice, st));
+    E_CUDA(e, cudaEventRecord(e->stage_evt[slot], st));
+    return BF_OK;
+}
+
+extern "C" int bf_engine_step(bf_engine* e, const float* packed, int n, int phases, void* stream) {
+    if (!e || n < 0 || n > e->cfg.max_det) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_step", "bad argument");
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phases == 0) phases = e_full_mask(e);
+    if (phases & (1 << PH_INGEST)) {
+        if (!packed) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_step", "null keyframe");
+        const int rc = e_upload(e, packed, BF_KF_HEADER + (size_t)BF_KF_ROW * n, st);
+        if (rc) return rc;
+    }
+    return e_run(e, phases, st);
+}
+
+extern "C" int bf_engine_step_device(bf_engine* e, const float* packed_dev, int n, int phases, void* stream) {
+    if (!e || n < 0 || n > e->cfg.max_det) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_step_device", "bad argument");
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phases == 0) phases = e_full_mask(e);
+    if (phases & (1 << PH_INGEST)) {
+        if (!packed_dev) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_step_device", "null keyframe");
+        E_CUDA(e, cudaMemcpyAsync(e->in_dev, packed_dev, sizeof(float) * (BF_KF_HEADER + (size_t)BF_KF_ROW * n), cudaMemcpyDeviceToDevice, st));
+    }
+    return e_run(e, phases, st);
+}
+
+extern "C" int bf_engine_ingest_world(bf_engine* e, const float* header /*host, BF_KF_HEADER floats*/, const float* tensor_w,
+                                      const float* R_w, const float* scores, const float* box2d, const float* projxy, const float* uv,
+                                      int n, void* stream) {
+    if (!e || !header || n < 0 || n > e->cfg.max_det || (n > 0 && (!tensor_w || !R_w || !scores || !box2d || !projxy || !uv)))
+        return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_ingest_world", "bad argument");
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = e_upload(e, header, BF_KF_HEADER, st);
+    if (rc) return rc;
+    bf_world_rows w;
+    w.tensor = tensor_w; w.R = R_w; w.scores = scores; w.box2d = box2d; w.projxy = projxy; w.uv = uv;
+    bf_engine_ingest_world_kernel<<<bf_blocks(e->cfg.max_det, 64), 64, 0, st>>>(e_ctx(e), w);
+    E_LAUNCH_CHECK(e, "bf_engine_ingest_world_kernel");
+    return BF_OK;
+}
+
+__global__ void bf_engine_set_counts_kernel(bf_engine_ctx c, int N, int M) {
+    bf_engine_state* st = c.st;
+    st->N = N; st->M = M; st->n = 0; st->Nall = N; st->Nnms = 0; st->Nnew = N; st->first = 0; st->any_new = 0; st->B = 0; st->pad[1] = 0;
+}
+
+extern "C" int bf_engine_set_counts(bf_engine* e, int N, int M, void* stream) {
+    if (!e || N < 0 || M < 0 || N > e->cfg.map_capacity || M > e->cfg.store_capacity) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_set_counts", "bad argument");
+    bf_device_guard guard(e->h);
+    bf_engine_set_counts_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e_ctx(e), N, M);
+    E_LAUNCH_CHECK(e, "bf_engine_set_counts_kernel");
+    return BF_OK;
+}
+
+extern "C" int bf_engine_read_state(bf_engine* e, bf_engine_state* out, void* stream) {
+    if (!e || !out) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_read_state", "bad argument");
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    E_CUDA(e, cudaMemcpyAsync(out, e->state, sizeof(bf_engine_state), cudaMemcpyDeviceToHost, st));
+    E_CUDA(e, cudaStreamSynchronize(st));
+    return BF_OK;
+}
+
+extern "C" int bf_engine_read_flags(bf_engine* e, int32_t* keep, int32_t* success, int count, bf_engine_state* state, void* stream) {
+    if (!e || count < 0 || count > e->cfg.map_capacity) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_read_flags", "bad argument");
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (keep && count) E_CUDA(e, cudaMemcpyAsync(keep, e->keep, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    if (success && count) E_CUDA(e, cudaMemcpyAsync(success, e->success, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    if (state) E_CUDA(e, cudaMemcpyAsync(state, e->state, sizeof(bf_engine_state), cudaMemcpyDeviceToHost, st));
+    E_CUDA(e, cudaStreamSynchronize(st));
+    return BF_OK;
+}
+
+extern "C" int bf_engine_pointers(bf_engine* e, int32_t** keep, int32_t** success, bf_engine_state** state_dev, int32_t** refine_iters,
+                                  int32_t** todo) {
+    if (!e) return BF_ERR_INVALID_ARG;
+    if (keep) *keep = e->keep;
+    if (success) *success = e->success;
+    if (state_dev) *state_dev = e->state;
+    if (refine_iters) *refine_iters = e->its;
+    if (todo) *todo = e->todo;
+    return BF_OK;
+}
+
+extern "C" int bf_engine_launch_counts(bf_engine* e, int32_t* counts /*[8]: per phase bit, then the whole keyframe*/) {
+    if (!e || !counts) return BF_ERR_INVALID_ARG;
+    for (int p = 0; p < PH_COUNT + 1; ++p) counts[p] = e->launches[p];
     return BF_OK;
 }

@@ -2,17 +2,17 @@
 // pose disparity (A8).  All float32 with the reference's rounding order made explicit through
 // __fmul_rn/__fadd_rn (torch's CPU bmm on 3x3 operands rounds as ((a0*b0 + a1*b1) + a2*b2), no FMA),
 // so results are bit-identical to the reference's CPU tensors.
-#include "bf_common.cuh"
+#include "bf_internal.cuh"
 
 __device__ __forceinline__ float dot3_seq(float a0, float b0, float a1, float b1, float a2, float b2) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
 }
 
 // boxes.py:725-778.  One thread per box: 15 floats in, 24 (+3) out.
-__global__ void bf_corners_kernel(const float* __restrict__ xyzlhw, const float* __restrict__ R, int N,
+__global__ void bf_corners_kernel(const float* __restrict__ xyzlhw, const float* __restrict__ R, const bf_dimref Nd,
                                   float* __restrict__ corners, float* __restrict__ centers) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int N = bf_dim(Nd);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     const float* t = xyzlhw + 6 * n;
     const float* r = R + 9 * n;
     const float hl = t[3] * 0.5f, hh = t[4] * 0.5f, hw = t[5] * 0.5f;   // x/2 is exact
@@ -41,15 +41,24 @@ __global__ void bf_corners_kernel(const float* __restrict__ xyzlhw, const float*
         centers[3 * n + 1] = sum[1] * 0.125f;
         centers[3 * n + 2] = sum[2] * 0.125f;
     }
+    }
+}
+
+int bf_box_corners_run(bf_handle* h, const float* xyzlhw, const float* R, bf_dimref Nd, float* corners, float* centers, cudaStream_t st) {
+    int g = bf_blocks(Nd.host, 128);
+    if (g > h->sm_count * 4) g = h->sm_count * 4;
+    if (g < 1) g = 1;
+    bf_corners_kernel<<<g, 128, 0, st>>>(xyzlhw, R, Nd, corners, centers);
+    BF_LAUNCH_CHECK(h, "bf_corners_kernel");
+    return BF_OK;
 }
 
 extern "C" int bf_box_corners(bf_handle* h, const float* xyzlhw, const float* R, int N, float* corners,
                               float* centers, void* stream) {
+    bf_device_guard guard(h);
     if (!h || N < 0 || (N > 0 && (!xyzlhw || !R || !corners))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_box_corners", "bad argument");
     if (N == 0) return BF_OK;
-    bf_corners_kernel<<<bf_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, R, N, corners, centers);
-    BF_LAUNCH_CHECK(h, "bf_corners_kernel");
-    return BF_OK;
+    return bf_box_corners_run(h, xyzlhw, R, bf_dim_host(N), corners, centers, (cudaStream_t)stream);
 }
 
 // boxes.py:825-833, in place.
@@ -74,6 +83,7 @@ __global__ void bf_transform2world_kernel(float* __restrict__ xyzlhw, float* __r
 }
 
 extern "C" int bf_transform2world(bf_handle* h, float* xyzlhw, float* R, const float* poses, int N, void* stream) {
+    bf_device_guard guard(h);
     if (!h || N < 0 || (N > 0 && (!xyzlhw || !R || !poses))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_transform2world", "bad argument");
     if (N == 0) return BF_OK;
     bf_transform2world_kernel<<<bf_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, R, poses, N);
@@ -102,6 +112,7 @@ __global__ void bf_project_kernel(const float* __restrict__ corners, const float
 
 extern "C" int bf_project_boxes(bf_handle* h, const float* corners, const float* pose_inv, int N, float fx, float fy,
                                 float cx, float cy, float W, float H, float* uv, void* stream) {
+    bf_device_guard guard(h);
     if (!h || N < 0 || (N > 0 && (!corners || !pose_inv || !uv))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_project_boxes", "bad argument");
     if (N == 0) return BF_OK;
     bf_project_kernel<<<bf_blocks(8LL * N, 128), 128, 0, (cudaStream_t)stream>>>(corners, pose_inv, N, fx, fy, cx, cy, W, H, uv);
@@ -128,6 +139,7 @@ __global__ void bf_pose_disparity_kernel(const float* __restrict__ poses, const 
 
 extern "C" int bf_pose_disparity(bf_handle* h, const float* poses, const int32_t* ia, const int32_t* ib, int n,
                                  float* baseline, float* angle_deg, void* stream) {
+    bf_device_guard guard(h);
     if (!h || n < 0 || (n > 0 && (!poses || !ia || !ib || !baseline || !angle_deg))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_pose_disparity", "bad argument");
     if (n == 0) return BF_OK;
     bf_pose_disparity_kernel<<<bf_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(poses, ia, ib, n, baseline, angle_deg);
@@ -168,6 +180,7 @@ __global__ void bf_detection_filter_kernel(const float* __restrict__ xyzlhw, con
 extern "C" int bf_detection_filter(bf_handle* h, const float* xyzlhw, const float* proj_xy, const float* scores, int n,
                                    float score_thresh, int use_uv, double uv_ratio, float W, float H, int use_floor, float floor_ratio,
                                    int use_large, float size_max, int32_t* flags, int32_t* keep, void* stream) {
+    bf_device_guard guard(h);
     if (!h || n < 0 || (n > 0 && (!xyzlhw || !proj_xy || !scores || !flags || !keep)))
         return bf_fail(h, BF_ERR_INVALID_ARG, "bf_detection_filter", "bad argument");
     if (n == 0) return BF_OK;

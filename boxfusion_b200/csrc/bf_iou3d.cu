@@ -15,10 +15,10 @@ struct bf_work_item { int a, b; };
 
 // ------------------------------------------------------------------------------------------------
 // One thread per (box, face): the two triangle planes of that face; the first thread of a box also writes the AABB.
-__global__ void bf_planes_kernel(const float* __restrict__ corners, int N, double* __restrict__ planes,
+__global__ void bf_planes_kernel(const float* __restrict__ corners, const bf_dimref Nd, double* __restrict__ planes,
                                  float* __restrict__ aabb) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 6 * N) return;
+    const int N = bf_dim(Nd);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 6 * N; t += gridDim.x * blockDim.x) {
     const int n = t / 6, f = t - 6 * n;
     float c[24];
 #pragma unroll
@@ -35,6 +35,7 @@ __global__ void bf_planes_kernel(const float* __restrict__ corners, int N, doubl
             for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], c[3 * i + k]); hi[k] = fmaxf(hi[k], c[3 * i + k]); }
 #pragma unroll
         for (int k = 0; k < 3; ++k) { aabb[6 * n + k] = lo[k]; aabb[6 * n + 3 + k] = hi[k]; }
+    }
     }
 }
 
@@ -124,54 +125,60 @@ __device__ inline bool bf_analytic_iou(const float* __restrict__ ca, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// One thread per pair.  triangle != 0: A and B are the same set and only a < b is evaluated (NMS).
+// One thread per pair (grid-stride).  triangle != 0: A and B are the same set and only a < b is evaluated (NMS).
 // Outputs: dense iou/counts zero-filled (when given), work list of gate-passing pairs, stats.
 // counters: [0] work items, [1] pairs, [2] AABB-passing, [3] gate-passing, [4] analytic, [5] overflow, [6] NMS edges
+// M / N are host values or read from device memory (bf_dimref); the mask row stride is W = ceil(N/32) of the actual N.
 __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA,
-                                const double* __restrict__ planesA, int M, const float* __restrict__ cornersB,
-                                const float* __restrict__ aabbB, const double* __restrict__ planesB, int N,
+                                const double* __restrict__ planesA, const bf_dimref Md, const float* __restrict__ cornersB,
+                                const float* __restrict__ aabbB, const double* __restrict__ planesB, const bf_dimref Nd,
                                 int triangle, int mode, double* __restrict__ iou, int32_t* __restrict__ counts,
                                 bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
                                 // NMS outputs (ANALYTIC hits are thresholded here)
                                 double thr, const int32_t* __restrict__ rank, uint32_t* __restrict__ mask,
-                                uint32_t* __restrict__ rowany, int W, unsigned long long* __restrict__ edges, int edge_cap) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                uint32_t* __restrict__ rowany, unsigned long long* __restrict__ edges, int edge_cap) {
+    const int M = bf_dim(Md), N = bf_dim(Nd);
+    const int W = (N + 31) >> 5;
     const long long total = (long long)M * N;
-    if (p >= total) return;
-    if (p == 0) counters[1] = triangle ? (unsigned long long)M * (unsigned long long)(M - 1) / 2ULL : (unsigned long long)total;
-    const int a = (int)(p / N), b = (int)(p % N);
-    if (iou) iou[p] = 0.0;
-    if (counts) { counts[3 * p] = 0; counts[3 * p + 1] = 0; counts[3 * p + 2] = 0; }
-    if (triangle && a >= b) return;
-    // exact reject: a point within 1e-6 of every face plane of a box lies within its AABB grown by 1e-4
-    const float* ba = aabbA + 6 * a;
-    const float* bb = aabbB + 6 * b;
-    const float m = 1e-4f;
-    if (ba[0] > bb[3] + m || bb[0] > ba[3] + m || ba[1] > bb[4] + m || bb[1] > ba[4] + m || ba[2] > bb[5] + m ||
-        bb[2] > ba[5] + m)
-        return;
-    atomicAdd(&counters[2], 1ULL);
-    const float* ca = cornersA + 24 * a;
-    const float* cb = cornersB + 24 * b;
-    if (mode == BF_IOU_ANALYTIC) {
-        double v;
-        if (bf_analytic_iou(ca, cb, &v)) {
-            atomicAdd(&counters[4], 1ULL);
-            if (iou) iou[p] = v;
-            if (mask && v > thr) {
-                const int ra = rank[a], rb = rank[b];
-                const int r0 = min(ra, rb), r1 = max(ra, rb);
-                atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
-                atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
-                const unsigned long long e = atomicAdd(&counters[6], 1ULL);
-                if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
+    const long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p0 == 0) counters[1] = triangle ? (unsigned long long)M * (unsigned long long)(M > 0 ? M - 1 : 0) / 2ULL : (unsigned long long)total;
+    for (long long p = p0; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(p / N), b = (int)(p % N);
+        if (iou) iou[p] = 0.0;
+        if (counts) { counts[3 * p] = 0; counts[3 * p + 1] = 0; counts[3 * p + 2] = 0; }
+        if (triangle && a >= b) continue;
+        // exact reject: a point within 1e-6 of every face plane of a box lies within its AABB grown by 1e-4
+        const float* ba = aabbA + 6 * a;
+        const float* bb = aabbB + 6 * b;
+        const float m = 1e-4f;
+        if (ba[0] > bb[3] + m || bb[0] > ba[3] + m || ba[1] > bb[4] + m || bb[1] > ba[4] + m || ba[2] > bb[5] + m ||
+            bb[2] > ba[5] + m)
+            continue;
+        atomicAdd(&counters[2], 1ULL);
+        const float* ca = cornersA + 24 * a;
+        const float* cb = cornersB + 24 * b;
+        if (mode == BF_IOU_ANALYTIC) {
+            double v;
+            if (bf_analytic_iou(ca, cb, &v)) {
+                atomicAdd(&counters[4], 1ULL);
+                if (iou) iou[p] = v;
+                if (rank && v > thr) {
+                    const int ra = rank[a], rb = rank[b];
+                    const int r0 = min(ra, rb), r1 = max(ra, rb);
+                    if (mask) {
+                        atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
+                        atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
+                    }
+                    const unsigned long long e = atomicAdd(&counters[6], 1ULL);
+                    if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
+                }
+                continue;
             }
-            return;
         }
+        const unsigned long long slot = atomicAdd(&counters[0], 1ULL);      // candidate: gate + counts in bf_count_kernel
+        if (slot < (unsigned long long)work_cap) { work[slot].a = a; work[slot].b = b; }
+        else atomicExch(&counters[5], 1ULL);
     }
-    const unsigned long long slot = atomicAdd(&counters[0], 1ULL);      // candidate: gate + counts in bf_count_kernel
-    if (slot < (unsigned long long)work_cap) { work[slot].a = a; work[slot].b = b; }
-    else atomicExch(&counters[5], 1ULL);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,10 +187,12 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
 __global__ void __launch_bounds__(BF_COUNT_THREADS)
 bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA, const double* __restrict__ planesA,
                 const float* __restrict__ cornersB, const float* __restrict__ aabbB, const double* __restrict__ planesB,
-                int N, const bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
+                const bf_dimref Nd, const bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
                 double* __restrict__ iou, int32_t* __restrict__ counts, double thr, const int32_t* __restrict__ rank,
-                uint32_t* __restrict__ mask, uint32_t* __restrict__ rowany, int W, unsigned long long* __restrict__ edges,
+                uint32_t* __restrict__ mask, uint32_t* __restrict__ rowany, unsigned long long* __restrict__ edges,
                 int edge_cap) {
+    const int N = bf_dim(Nd);
+    const int W = (N + 31) >> 5;
     __shared__ double s_pl[2][48];
     __shared__ double s_grid[3][BF_NS];
     __shared__ float s_c[2][24];
@@ -244,11 +253,13 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
             const size_t p = (size_t)a * N + b;
             if (iou) iou[p] = v;
             if (counts) { counts[3 * p] = n1; counts[3 * p + 1] = n2; counts[3 * p + 2] = n12; }
-            if (mask && v > thr) {
+            if (rank && v > thr) {
                 const int ra = rank[a], rb = rank[b];
                 const int r0 = min(ra, rb), r1 = max(ra, rb);
-                atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
-                atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
+                if (mask) {
+                    atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
+                    atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
+                }
                 const unsigned long long e = atomicAdd(&counters[6], 1ULL);
                 if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
             }
@@ -257,41 +268,57 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Host driver shared by bf_iou3d_matrix and bf_nms3d.
-int bf_iou3d_run(bf_handle* h, const float* cornersA, int M, const float* cornersB, int N, int triangle, int mode,
+// Host driver shared by bf_iou3d_matrix, bf_nms3d and the engine step.  Md / Nd: sizes on the host, or upper bounds on
+// the host + the actual sizes in device memory (the captured engine step: scratch is sized for the bounds, the grids are
+// fixed and the kernels stride).  The counters are zeroed here.
+int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float* cornersB, bf_dimref Nd, int triangle, int mode,
                  double* iou, int32_t* counts, int64_t* stats, double thr, const int32_t* rank, uint32_t* mask,
-                 uint32_t* rowany, int W, unsigned long long* edges, int edge_cap, cudaStream_t st) {
+                 uint32_t* rowany, unsigned long long* edges, int edge_cap, cudaStream_t st) {
     double *plA = nullptr, *plB = nullptr;
     float *bbA = nullptr, *bbB = nullptr;
     int rc;
     void* p;
+    const int M = Md.host, N = Nd.host;                   // sizing values (bounds when the real sizes are on the device)
+    const bool dev_sized = Md.dev || Nd.dev;
+    const int stride_grid = h->sm_count * 8;
     if ((rc = bf_scratch(h, BF_SCRATCH_PLANES_A, sizeof(double) * 48 * (size_t)M, &p))) return rc; plA = (double*)p;
     if ((rc = bf_scratch(h, BF_SCRATCH_AABB_A, sizeof(float) * 6 * (size_t)M, &p))) return rc; bbA = (float*)p;
-    bf_planes_kernel<<<bf_blocks(6LL * M, 96), 96, 0, st>>>(cornersA, M, plA, bbA);
+    {
+        const int g = bf_blocks(6LL * M, 96);
+        bf_planes_kernel<<<(dev_sized && g > stride_grid) ? stride_grid : g, 96, 0, st>>>(cornersA, Md, plA, bbA);
+    }
     BF_LAUNCH_CHECK(h, "bf_planes_kernel");
-    if (cornersB == cornersA && N == M) { plB = plA; bbB = bbA; }
+    if (cornersB == cornersA && Nd.host == Md.host && Nd.dev == Md.dev) { plB = plA; bbB = bbA; }
     else {
         if ((rc = bf_scratch(h, BF_SCRATCH_PLANES_B, sizeof(double) * 48 * (size_t)N, &p))) return rc; plB = (double*)p;
         if ((rc = bf_scratch(h, BF_SCRATCH_AABB_B, sizeof(float) * 6 * (size_t)N, &p))) return rc; bbB = (float*)p;
-        bf_planes_kernel<<<bf_blocks(6LL * N, 96), 96, 0, st>>>(cornersB, N, plB, bbB);
+        const int g = bf_blocks(6LL * N, 96);
+        bf_planes_kernel<<<(dev_sized && g > stride_grid) ? stride_grid : g, 96, 0, st>>>(cornersB, Nd, plB, bbB);
         BF_LAUNCH_CHECK(h, "bf_planes_kernel");
     }
     const long long total = (long long)M * N;
     // work-list capacity: every pair for small problems, else 64 candidates per box (grown on overflow)
     long long cap = total < (1LL << 20) ? total : (1LL << 20) + 64LL * (M + N);
-    if ((long long)(h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item)) > cap) cap = h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item);
+    if ((long long)(h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item)) > cap || h->frozen) cap = h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item);
     if (cap > 0x7fffffffLL) cap = 0x7fffffffLL;
     if ((rc = bf_scratch(h, BF_SCRATCH_WORK, sizeof(bf_work_item) * (size_t)cap, &p))) return rc;
     bf_work_item* work = (bf_work_item*)p;
     if ((rc = bf_scratch(h, BF_SCRATCH_COUNTERS, sizeof(unsigned long long) * 8, &p))) return rc;
     unsigned long long* counters = (unsigned long long*)p;
     BF_CUDA(h, cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 8, st));
-    bf_pairs_kernel<<<bf_blocks(total, 128), 128, 0, st>>>(cornersA, bbA, plA, M, cornersB, bbB, plB, N, triangle, mode,
-                                                           iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, W, edges, edge_cap);
+    {
+        // fixed, machine-filling grid when the sizes live on the device; exact grid otherwise (capped: the kernel strides)
+        long long g = (total + 127) / 128;
+        const long long gcap = (long long)h->sm_count * (dev_sized ? 16 : 64);
+        if (g > gcap) g = gcap;
+        if (g < 1) g = 1;
+        bf_pairs_kernel<<<(unsigned)g, 128, 0, st>>>(cornersA, bbA, plA, Md, cornersB, bbB, plB, Nd, triangle, mode,
+                                                     iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, edges, edge_cap);
+    }
     BF_LAUNCH_CHECK(h, "bf_pairs_kernel");
     const int grid = h->sm_count * 8;
-    bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, N, work, (int)cap, counters,
-                                                       iou, counts, thr, rank, mask, rowany, W, edges, edge_cap);
+    bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, Nd, work, (int)cap, counters,
+                                                       iou, counts, thr, rank, mask, rowany, edges, edge_cap);
     BF_LAUNCH_CHECK(h, "bf_count_kernel");
     if (stats)   // pairs, AABB-passing, gate-passing, analytic
         BF_CUDA(h, cudaMemcpyAsync(stats, counters + 1, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
@@ -310,14 +337,15 @@ int bf_iou3d_overflowed(bf_handle* h, cudaStream_t st, int* overflow) {
 
 extern "C" int bf_iou3d_matrix(bf_handle* h, const float* cornersA, int M, const float* cornersB, int N, int mode,
                                double* iou, int32_t* counts, int64_t* stats, void* stream) {
+    bf_device_guard guard(h);
     if (!h || M < 0 || N < 0 || (mode != BF_IOU_SAMPLED_REF && mode != BF_IOU_ANALYTIC))
         return bf_fail(h, BF_ERR_INVALID_ARG, "bf_iou3d_matrix", "bad argument");
     if (M == 0 || N == 0) return BF_OK;
     if (!cornersA || !cornersB || !iou) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_iou3d_matrix", "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        int rc = bf_iou3d_run(h, cornersA, M, cornersB, N, 0, mode, iou, counts, stats, 0.0, nullptr,
-                              nullptr, nullptr, 0, nullptr, 0, st);
+        int rc = bf_iou3d_run(h, cornersA, bf_dim_host(M), cornersB, bf_dim_host(N), 0, mode, iou, counts, stats, 0.0, nullptr,
+                              nullptr, nullptr, nullptr, 0, st);
         if (rc) return rc;
         if ((long long)M * N <= (long long)(h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item))) break;   // cannot overflow
         int ovf = 0;
@@ -347,6 +375,7 @@ __global__ void bf_points_in_hull_kernel(const float* __restrict__ corners, cons
 }
 
 extern "C" int bf_points_in_hull(bf_handle* h, const float* corners, const double* points, int n, uint8_t* inside, void* stream) {
+    bf_device_guard guard(h);
     if (!h || n < 0 || (n > 0 && (!corners || !points || !inside))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_points_in_hull", "bad argument");
     if (n == 0) return BF_OK;
     bf_points_in_hull_kernel<<<bf_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(corners, points, n, inside);

@@ -20,9 +20,8 @@ MAX_VIEWS = 64
 
 # kernels launched by one call of each entry point (the library's own __global__ functions)
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
-                    "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 3, "bf_evaluate_iou": 1,
-                    "bf_engine_ingest": 1, "bf_engine_corr": 1, "bf_engine_compact": 2, "bf_engine_select": 1,
-                    "bf_engine_apply": 1, "bf_detection_filter": 1, "bf_score_order": 1, "bf_points_in_hull": 1}
+                    "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 1, "bf_evaluate_iou": 1,
+                    "bf_detection_filter": 1, "bf_score_order": 1, "bf_points_in_hull": 1, "bf_engine_ingest_world": 1}
 
 
 class Profile:
@@ -249,7 +248,7 @@ def points_in_hull(points, corners) -> torch.Tensor:
     return out.to(torch.bool)
 
 
-ORDER_MAX = 4096
+ORDER_MAX = 65536
 
 
 def score_order(scores) -> torch.Tensor:
@@ -258,7 +257,7 @@ def score_order(scores) -> torch.Tensor:
     s = dev_tensor(scores, torch.float32, dev).reshape(-1)
     n = s.shape[0]
     if n > ORDER_MAX:
-        return torch.argsort(s, descending=True, stable=True).to(torch.int32)
+        raise RuntimeError(f"score_order: {n} boxes; the device sort handles up to {ORDER_MAX}")
     order = torch.empty(n, dtype=torch.int32, device=dev)
     h = handle(dev)
     _call(h, "bf_score_order", h.lib.bf_score_order, h.h, ptr(s), n, ptr(order), h.stream())

@@ -84,7 +84,8 @@ int bf_iou3d_matrix(bf_handle* h, const float* cornersA /*[M,8,3]*/, int M, cons
  *   poses      [M,16]: per-frame camera poses indexed by the values stored in the fusion lists
  *   fusion_list[N,BF_FUSION_CAP] / fusion_len[N] / fusion_flag[N] (int32): in/out, rows kept sorted
  * outputs (int32, device): keep[N] 0/1, success[N] 0/1 (heads that suppressed something; valid_num += 1),
- *   status[1]: 0 or BF_ERR_CAPACITY if a fusion list overflowed BF_FUSION_CAP.
+ *   status[1]: set to BF_ERR_CAPACITY if a fusion list overflowed BF_FUSION_CAP (or, for N > 16384, more than 8192
+ *   over-threshold pairs were found); STICKY - never cleared by the library, the caller zeroes it.
  * IoU uses `mode`; suppression is `iou > iou_threshold` evaluated in float64. */
 int bf_nms3d(bf_handle* h, const float* corners /*[N,8,3]*/, const float* centers /*[N,3]*/, int N,
              const int32_t* order, const int32_t* init_id, const float* poses, int M,
@@ -111,10 +112,10 @@ int bf_points_in_hull(bf_handle* h, const float* corners /*[8,3]*/, const double
                       uint8_t* inside /*[n]*/, void* stream);
 
 /* ---- A5  the score order of nms_3d, `order = scores.argsort()[::-1]` (instances.py:52), on the device --------
- * order[r] = index of the r-th highest score; equal scores keep ascending index (a stable descending sort, what the
- * Python binding obtains from torch.argsort(descending=True, stable=True); NumPy's own argsort is unstable for exact
- * ties).  NaN scores sort first, -0 == +0.  One CTA, bitonic network in shared memory: N <= 4096
- * (BF_ERR_INVALID_ARG beyond; callers with larger maps sort elsewhere). */
+ * order[r] = index of the r-th highest score; equal scores keep ascending index (a stable descending sort, what
+ * torch.argsort(descending=True, stable=True) gives; NumPy's own argsort is unstable for exact ties).
+ * NaN scores sort first, -0 == +0.  N <= 4096: one CTA, bitonic network in shared memory; larger N (up to 65536):
+ * every box is ranked by counting the smaller keys (tiles through shared memory, all SMs). */
 int bf_score_order(bf_handle* h, const float* scores /*[N]*/, int N, int32_t* order /*[N]*/, void* stream);
 
 /* ---- A8  BoxManager.compute_pose_disparity (box_manager.py:168-186), batched ------------------- */
@@ -126,6 +127,8 @@ int bf_pose_disparity(bf_handle* h, const float* poses /*[M,16]*/, const int32_t
  * view_offsets[b+1]) (CSR, int32) of the per-frame store.  All `iters` optimiser iterations run
  * inside one launch.  Float32 arithmetic with the same operation order as the reference kernel
  * (compiled without FMA contraction), line intersections in float64, global box state in float64.
+ * status[1] is set to BF_ERR_CAPACITY when a box has fewer than 1 / more than max_views views (that box is skipped)
+ * or an intersection polygon exceeded the reference's own 36-candidate buffer; sticky, the caller zeroes it.
  */
 typedef struct {
     int32_t iters;            /* box_fusion.iters (20)                                   */
@@ -153,7 +156,10 @@ int bf_refine(bf_handle* h, const float* pst /*[P,6]*/, int P,
  * (independent sequences, bench.py --workload c5); small bf_refine calls then use 256-thread CTAs of the 80-register
  * instantiation, which can share an SM with another stream's kernels, instead of the shape that minimises the latency of
  * a lone call (+11 % keyframes/s with 8 concurrent sequences per GPU).  Results are identical.  No reference counterpart. */
-enum { BF_OPT_REFINE_CONCURRENT = 1 };
+enum { BF_OPT_REFINE_CONCURRENT = 1,
+       /* value G > 0: stand-alone bf_refine calls use the engine's launch shape - at most G persistent clusters of 16 CTAs
+        * x 512 threads, each looping over boxes - instead of one cluster per box (tests; 0 restores the default) */
+       BF_OPT_REFINE_PERSISTENT = 2 };
 int bf_set_option(bf_handle* h, int key, int value);
 
 /* Diagnostic: how the last bf_refine call of this handle was launched: kernel instantiation * 1000000 (0 = latency
@@ -180,28 +186,114 @@ typedef struct {            /* BoxManager.already_fusion */
     int32_t* lists /*[cap,BF_FUSION_CAP]*/; int32_t* len; unsigned long long* hash; int32_t* count /*[1]*/; int32_t cap;
 } bf_fused_table;
 
-/* demo.py:216-221, 243/248, 253-254: lift + project the keyframe's n detections and append them to map rows [N,N+n)
- * and store rows [M,M+n).  packed = tensor_cam[n,6] R_cam[n,9] scores[n] box2d[n,4] projxy[n,2] pose[16] pose_inv[16]. */
-int bf_engine_ingest(bf_handle* h, const float* packed, int n, float fx, float fy, float cx, float cy, float W, float H,
-                     int frame_id, int box_count, int N, int M, int D, const bf_map_buffers* mp /*host*/,
-                     const bf_store_buffers* st /*host*/, int32_t* fflag, void* stream);
-/* instances.py:411-490 + box_manager.py:90-129 on the keep/success flags bf_nms3d produced; also applies valid_num += 1
- * of nms_3d (instances.py:72-73).  info[0] <- 1 if any new box survived nms_3d (demo.py:269). */
-int bf_engine_corr(bf_handle* h, const bf_map_buffers* mp /*host*/, const float* store_poses, int32_t* fflag, int N_glo, int n,
-                   int32_t* keep, const int32_t* success, const float* pose_inv_np /*[16]*/, float fx, float fy, float cx,
-                   float cy, float W, float H, float small_size, float small_plus, double threshold, float translation_gap,
-                   float rotation_gap, int32_t* info, int32_t* status, void* stream);
-/* `all_pred_box[keep_idx]` + `box_manager.update(keep_idx)` (demo.py:292, 325-327): stable compaction of every map
- * field from `from` into `to`; info[1] <- new row count. */
-int bf_engine_compact(bf_handle* h, const int32_t* keep, int N, const bf_map_buffers* from /*host*/,
-                      const bf_map_buffers* to /*host*/, int32_t* info, void* stream);
-/* box_fusion.py:631-635: rows with >= 3 views whose view set was not fused before -> todo[], CSR for bf_refine;
- * info[2] = B, info[3] = sum of views, info[4] = max views, info[5] = status. */
-int bf_engine_select(bf_handle* h, const bf_map_buffers* mp /*host*/, const bf_fused_table* ft /*host*/, int32_t* info,
-                     int32_t* todo, int32_t* offsets, int32_t* view_index, void* stream);
-/* box_fusion.py:716-724: write bf_refine's rows into the map, set fusion flags, extend already_fusion. */
-int bf_engine_apply(bf_handle* h, const bf_map_buffers* mp /*host*/, const bf_fused_table* ft /*host*/, int32_t* fflag,
-                    const int32_t* info, const int32_t* todo, const float* out, const int32_t* upd, int32_t* status, void* stream);
+/* The engine: one keyframe of demo.py:200-327 per call, everything on the device.
+ *
+ * Round 2 replaced the per-kernel engine entries (ingest / corr / compact / select / apply, driven from Python with a
+ * mid-step 32-byte read-back) by ONE call per keyframe.  Every size that changes per keyframe (map rows N, store rows M,
+ * detections n, boxes to refine B, the intrinsics) lives in device memory (`bf_engine_state`, the keyframe header), the
+ * kernels read it themselves and run on fixed launch shapes, so the whole keyframe is ONE CUDA graph captured once per
+ * engine - ingest, 3-D NMS with record(), small-object correspondence, compaction, check_valid_num, selection,
+ * particle refinement, write-back - replayed with identical parameters: no host decision, no read-back and no torch
+ * call inside a keyframe.  The reference-shaped API (boxfusion_b200/instances.py etc.) replays the same phases as
+ * separate graphs and reads the keep flags in between, because spatial_association / correspondence_association
+ * return them to the caller (demo.py:262-289).
+ *
+ * The engine BORROWS the caller's map / store / fused buffers for its lifetime (they stay readable by the caller
+ * between steps: snapshot, export) and owns everything else, including a private bf_handle whose scratch is frozen
+ * once the graphs are captured.  One engine per sequence; engines are independent (own stream, own scratch). */
+typedef struct bf_engine bf_engine;
+
+typedef struct {
+    int32_t map_capacity;       /* rows of each map buffer set (<= 65536)                                   */
+    int32_t store_capacity;     /* rows of the per-frame store / fusion_flag                                */
+    int32_t max_det;            /* detections per keyframe bound (demo.py: topk_per_image = 100)            */
+    int32_t iou_mode;           /* BF_IOU_SAMPLED_REF | BF_IOU_ANALYTIC                                      */
+    double nms_threshold;       /* box_fusion.nms_threshold                                                 */
+    double small_threshold;     /* association.small_threshold                                              */
+    float translation_gap, rotation_gap, center_gap;    /* association.* , 0.5 (box_manager.py:55)          */
+    float small_size, small_plus;                         /* box_fusion.small_size and float32(small_size + 0.1) */
+    int32_t use_fusion;         /* box_fusion.use                                                           */
+    int32_t check_valid;        /* box_fusion.check_valid (demo.py:297-298)                                 */
+    int32_t gap;                /* data.gap in FRAMES, compared with frame ids (box_manager.py:151-166)     */
+    int32_t use_graph;          /* 1: replay captured CUDA graphs; 0: issue the same launches eagerly       */
+    bf_refine_cfg refine;       /* optimiser constants; the intrinsics fields are ignored (per keyframe)    */
+    const float* pst;           /* particle template [P,6], device, borrowed                                */
+    int32_t P;
+} bf_engine_cfg;
+
+typedef struct {                /* caller-owned device buffers, borrowed for the engine's lifetime */
+    bf_map_buffers map[2];      /* ping-pong for the compactions; state.cur says which one is current */
+    bf_store_buffers store;
+    int32_t* fusion_flag;       /* [store_capacity] BoxManager.fusion_flag (never re-indexed, like the reference) */
+    bf_fused_table fused;
+} bf_engine_buffers;
+
+typedef struct {                /* the engine's counters, device-resident; bf_engine_read_state copies them out */
+    int32_t N;                  /* map rows (len(all_pred_box))                                             */
+    int32_t M;                  /* store rows (= box_count = len(per_frame_ins) = len(fusion_flag))         */
+    int32_t cur;                /* which map buffer set is current                                          */
+    int32_t steps;              /* keyframes with detections processed                                      */
+    int32_t n;                  /* detections of the keyframe in flight / last processed                    */
+    int32_t Nall;               /* N + n while the keyframe is in flight                                    */
+    int32_t Nnms;               /* Nall, or 0 on the first keyframe (no association, demo.py:228-243)       */
+    int32_t first;              /* the keyframe in flight is the first one                                  */
+    int32_t any_new;            /* a new box survived nms_3d (demo.py:269)                                  */
+    int32_t Nnew;               /* rows after the last compaction                                           */
+    int32_t B, SV, maxV;        /* refinement of the last keyframe: boxes, sum of views, max views          */
+    int32_t status[8];          /* sticky BF_ERR_*: [0] nms lists [1] corr lists [2] refine [3] fused table [4] capacity of map/store
+                                   [5] views > BF_MAX_VIEWS [6] IoU work list overflow [7] reserved */
+    int32_t refine_boxes_total; /* running sums for accounting */
+    int32_t refine_views_total;
+    int32_t pad[9];
+} bf_engine_state;              /* 32 x int32 */
+
+/* Keyframe as the host hands it over: one packed float32 buffer
+ *   [0] n (as int32 bits) [1] frame id (int32 bits; demo.py:217) [2..7] fx fy cx cy W H
+ *   [8..23] pose (camera->world) [24..39] torch.linalg.inv(pose) (instances.py:350) [40..55] np.linalg.inv(pose) (instances.py:680)
+ *   then tensor_cam[n,6] R_cam[n,9] scores[n] box2d[n,4] projxy[n,2]. */
+#define BF_KF_HEADER 56
+#define BF_KF_ROW 22
+
+int bf_engine_create(int device, const bf_engine_cfg* cfg, const bf_engine_buffers* bufs, bf_engine** out);
+void bf_engine_destroy(bf_engine* e);
+const char* bf_engine_last_error(bf_engine* e);
+/* new sequence in the same buffers */
+int bf_engine_reset(bf_engine* e, void* stream);
+/* One keyframe, asynchronous.  `phases` selects what runs (0 = the whole keyframe as the engine's configuration defines
+ * it: one graph launch):
+ *   bit 0  ingest: copy `packed` (HOST memory, BF_KF_HEADER + BF_KF_ROW * n floats; consumed before the call returns) to
+ *          the device, lift + project + append                       (demo.py:216-221, 243/248, 253-254)
+ *   bit 1  spatial association: corners, score order, 3-D NMS with record()        (demo.py:262)
+ *   bit 2  correspondence association incl. record_corr                           (demo.py:273-289)
+ *   bit 3  all_pred_box[keep_idx] + box_manager.update                            (demo.py:292, 325-327)
+ *   bit 4  BoxManager.check_valid_num                                             (demo.py:297-298)
+ *   bit 5  BoxFusion.boxfusion: selection, particle refinement, write-back         (demo.py:304-305)
+ *   bit 6  close the keyframe (row counters for the next one)
+ * The bits of one keyframe must be issued in ascending order, on one stream per engine.  The reference-shaped API issues
+ * them call by call and reads the keep flags in between (bf_engine_read_flags); the engine's own step passes 0. */
+int bf_engine_step(bf_engine* e, const float* packed /*host*/, int n, int phases, void* stream);
+/* Same with the packed keyframe already in device memory (no host copy). */
+int bf_engine_step_device(bf_engine* e, const float* packed_dev, int n, int phases, void* stream);
+/* Bit 0 for detections the caller lifted and projected itself (the reference-shaped API: transform2world and
+ * project_3d_boxes are separate calls there): row copies from the caller's device tensors; `header` (HOST,
+ * BF_KF_HEADER floats) carries n, frame id, intrinsics, pose and np.linalg.inv(pose). */
+int bf_engine_ingest_world(bf_engine* e, const float* header /*host*/, const float* tensor_w /*[n,6]*/, const float* R_w /*[n,9]*/,
+                           const float* scores /*[n]*/, const float* box2d /*[n,4]*/, const float* projxy /*[n,2]*/,
+                           const float* uv /*[n,16]*/, int n, void* stream);
+/* The caller filled the first N map rows / M store rows (and the fused table) itself - state imported from the
+ * reference-shaped containers: set the row counters accordingly (between keyframes only). */
+int bf_engine_set_counts(bf_engine* e, int N, int M, void* stream);
+/* Copies the state words to host memory and waits for the stream. */
+int bf_engine_read_state(bf_engine* e, bf_engine_state* out /*host*/, void* stream);
+/* keep / success flags of the keyframe in flight (first `count` rows) and the state words to HOST memory in one
+ * synchronisation (any pointer may be NULL). */
+int bf_engine_read_flags(bf_engine* e, int32_t* keep /*host*/, int32_t* success /*host*/, int count, bf_engine_state* state /*host*/,
+                         void* stream);
+/* Device pointers of engine-owned per-keyframe results (valid for the engine's lifetime). */
+int bf_engine_pointers(bf_engine* e, int32_t** keep, int32_t** success, bf_engine_state** state_dev, int32_t** refine_iters,
+                       int32_t** todo);
+/* kernels launched per phase bit (counts[0..6]) and by the whole keyframe (counts[7]) */
+int bf_engine_launch_counts(bf_engine* e, int32_t* counts /*[8]*/);
 
 /* ---- Detection pre-filters in one pass (demo.py:138-148) -------------------------
  * score >= score_thresh, BoxManager.check_uv_bounds (box_manager.py:217-225, uv_ratio is the Python double),

@@ -101,6 +101,49 @@ def test_check_valid_num_three_way():
     assert dropped > 0, "the scene must exercise check_valid_num"
 
 
+def test_engine_graph_equals_eager_and_phase_by_phase():
+    """The captured whole-keyframe graph, the same launches issued eagerly, and the keyframe issued phase by phase (what the
+    reference-shaped API does) leave identical state."""
+    from boxfusion_b200 import _lib
+    scene = SyntheticScene(n_objects=80, seed=31, max_det=30, shape="ca1m", tilt_noise=0.01)
+    cfg = make_cfg("ca1m", pst_path=make_pst(256, seed=2), pst_size=256)
+    mk = lambda **kw: FusionEngine(cfg, map_capacity=512, store_capacity=2048, fused_capacity=512, **kw)   # noqa: E731
+    a, b, c = mk(), mk(use_graph=False), mk()
+    phases = [_lib.PH_INGEST, _lib.PH_NMS, _lib.PH_CORR, _lib.PH_COMPACT, _lib.PH_FUSE, _lib.PH_FINISH]
+    for k in range(25):
+        kf = scene.keyframe(k)
+        n = kf.tensor_cam.shape[0]
+        a.step(_pack(kf), n, kf.K, kf.image_size)
+        b.step(_pack(kf), n, kf.K, kf.image_size)
+        packed = _pack(kf)
+        for i, ph in enumerate(phases):
+            if n:
+                c.step(packed, n, kf.K if i == 0 else None, kf.image_size if i == 0 else None, k if i == 0 else None, phases=ph)
+        if not n:
+            c.step(packed, 0)
+        sa, sb, sc = a.snapshot(), b.snapshot(), c.snapshot()
+        for key in KEYS:
+            assert np.array_equal(_bits(sa[key]), _bits(sb[key])), ("graph vs eager", k, key)
+            assert np.array_equal(_bits(sa[key]), _bits(sc[key])), ("graph vs phases", k, key)
+    assert a.N > 20 and a.state().refine_boxes_total > 5 and a.M == c.M == b.M
+
+
+def test_engine_reset_reuses_buffers_and_graphs():
+    scene = SyntheticScene(n_objects=40, seed=3, max_det=16)
+    cfg = make_cfg("ca1m", pst_path=make_pst(256, seed=0), pst_size=256)
+    eng = FusionEngine(cfg, map_capacity=256, store_capacity=1024, fused_capacity=256)
+    snaps = []
+    for rep in range(2):
+        for k in range(8):
+            kf = scene.keyframe(k)
+            eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size)
+        snaps.append(eng.snapshot())
+        eng.reset()
+        assert eng.N == 0 and eng.M == 0
+    for key in KEYS:
+        assert np.array_equal(_bits(snaps[0][key]), _bits(snaps[1][key])), key
+
+
 def test_engine_empty_keyframe_and_capacity():
     scene = SyntheticScene(n_objects=20, seed=2, max_det=8)
     cfg = make_cfg("ca1m", pst_path=make_pst(64), pst_size=64)

@@ -204,6 +204,34 @@ def test_nms_dense_fallback_when_edge_list_overflows(monkeypatch):
     assert got[2] == ref[2] and np.array_equal(got[4], ref[4])
 
 
+def test_nms_dense_fallback_many_heads(monkeypatch):
+    """The dense path with several heads (record() runs in parallel over heads there too): piles of near-identical boxes,
+    multi-view lists and flags on some of them, > 8192 over-threshold pairs in total."""
+    monkeypatch.setattr(port, "IOU_BACKEND", "c")
+    rs = np.random.RandomState(5)
+    piles, per = 4, 70                                              # 4 * C(70,2) = 9660 pairs
+    n = piles * per
+    t = np.zeros((n, 6), np.float32)
+    for p in range(piles):
+        t[p * per:(p + 1) * per] = np.array([2.5 * p, -0.2, 0.9, 0.8, 0.6, 0.7], np.float32)
+    t[:, :3] += rs.normal(0, 0.02, (n, 3)).astype(np.float32)
+    R = np.tile(np.eye(3, dtype=np.float32), (n, 1, 1))
+    s = (rs.uniform(0.4, 1.0, n) + np.arange(n) * 1e-6).astype(np.float32)
+    lists, M = [], 0
+    for i in range(n):
+        k = int(rs.choice([1] * 22 + [2, 3]))                      # a few multi-view lists per pile (merged lists stay below the device cap)
+        lists.append(list(range(M, M + k))); M += k
+    poses = np.tile(np.eye(4, dtype=np.float32), (M, 1, 1))
+    ang = np.deg2rad(rs.uniform(0, 90, M))
+    poses[:, 0, 0], poses[:, 0, 1], poses[:, 1, 0], poses[:, 1, 1] = np.cos(ang), -np.sin(ang), np.sin(ang), np.cos(ang)
+    poses[:, :3, 3] = rs.uniform(-2, 2, (M, 3)).astype(np.float32)
+    flags = [int(rs.rand() < 0.5) if len(l) > 1 else 0 for l in lists]
+    case = (t, R, s, lists, flags, poses, np.array([l[0] for l in lists], dtype=np.int64))
+    got, ref = _run_nms(api, case), _run_nms(port, case)
+    assert got[0] == ref[0] and got[1] == ref[1] and len(ref[1]) >= piles
+    assert got[2] == ref[2] and got[3] == ref[3] and np.array_equal(got[4], ref[4])
+
+
 def test_nms_single_box_quirk():
     case = _nms_case(1, 0, 5)
     cfg = make_cfg("ca1m", pst_path=make_pst(32))
@@ -265,8 +293,12 @@ def test_score_order_matches_stable_descending_argsort():
         want = torch.argsort(t, descending=True, stable=True).to(torch.int32)
         got = ops.score_order(t)
         assert torch.equal(want, got), n
-    big = torch.rand(5000, device="cuda")                                       # beyond the single-CTA limit: torch path
-    assert torch.equal(ops.score_order(big), torch.argsort(big, descending=True, stable=True).to(torch.int32))
+    for n in (4097, 4352, 5000, 20000, 65536):                                  # beyond the single-CTA limit: rank by counting, all SMs
+        s = rs.uniform(0.0, 1.0, n).astype(np.float32)
+        s[rs.randint(0, n, n // 4)] = s[rs.randint(0, n, n // 4)]
+        s[1], s[5], s[3], s[7] = 0.0, -0.0, np.nan, -1.5
+        big = torch.from_numpy(s).cuda()
+        assert torch.equal(ops.score_order(big), torch.argsort(big, descending=True, stable=True).to(torch.int32)), n
 
 
 # ---- A16-A22 refinement ----------------------------------------------------------------------------------
@@ -333,6 +365,37 @@ def test_refine_matches_c_oracle(B, V, P, pst_size, variant):
         assert np.array_equal(_bits(trace[b, :n_it]), _bits(tr[:n_it]))       # per-iteration success/min_iou/search radii
         if u:
             assert np.array_equal(_bits(out[b]), _bits(o6))
+
+
+def test_refine_persistent_clusters_match_one_cluster_per_box():
+    """The engine's launch shape (G persistent clusters looping over boxes, box count read by the kernel) gives the same
+    trace and boxes as the default one-cluster-per-box launch, for G below, equal to and above the box count."""
+    from boxfusion_b200 import _lib
+    B, V, P = 7, 6, 512
+    prob = refine_problem(B, V, seed=77)
+    W, H = prob["size"]
+    pst = make_pst(P, seed=1)
+    cfg = make_cfg("ca1m", pst_path=pst, pst_size=P)
+    K16 = ro.K16_from_K3(prob["K"])
+    corners = ops.box_corners(prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 3, 3))
+    proj = ops.project_boxes(corners, torch.linalg.inv(torch.from_numpy(prob["poses"].reshape(-1, 4, 4))), prob["K"], W, H)
+    rcfg = ops.make_refine_cfg(cfg, K16, H, W)
+    off = np.arange(B + 1, dtype=np.int32) * V
+    idx = np.arange(B * V, dtype=np.int32)
+    args = (pst, prob["tensor"].reshape(-1, 6), prob["R"].reshape(-1, 9), prob["scores"].reshape(-1), proj,
+            prob["poses"].reshape(-1, 16), off, idx, rcfg)
+    ref = ops.refine(*args, want_trace=True, max_views=V)
+    h = _lib.handle()
+    try:
+        for G in (1, 3, 7, 64):
+            h.check(h.lib.bf_set_option(h.h, _lib.OPT_REFINE_PERSISTENT, G), "bf_set_option")
+            got = ops.refine(*args, want_trace=True, max_views=V)
+            assert ops.last_refine_launch() == {"variant": "latency", "cluster": 16, "threads": 512}
+            for a, b in zip(ref[:4], got[:4]):
+                assert torch.equal(a, b), G
+            assert int(got[4].item()) == 0
+    finally:
+        h.check(h.lib.bf_set_option(h.h, _lib.OPT_REFINE_PERSISTENT, 0), "bf_set_option")
 
 
 def test_refine_empty_and_capacity():

@@ -109,12 +109,15 @@ def test_detection_masks_match_the_port():
 def test_pack_keyframe_layout_and_replay_roundtrip(tmp_path):
     kf = SyntheticScene(n_objects=20, seed=1, max_det=7).keyframe(2)
     n = kf.tensor_cam.shape[0]
-    buf = pack_keyframe(kf.tensor_cam, kf.R_cam, kf.scores, kf.pred_boxes, kf.pred_proj_xy, kf.pose)
-    assert buf.dtype == np.float32 and buf.shape == (22 * n + 48,)
-    assert np.array_equal(buf[6 * n:15 * n].reshape(n, 3, 3), kf.R_cam) and np.array_equal(buf[15 * n:16 * n], kf.scores)
-    assert np.array_equal(buf[22 * n:22 * n + 16].reshape(4, 4), kf.pose)
-    assert np.array_equal(buf[22 * n + 16:22 * n + 32].reshape(4, 4), torch.linalg.inv(torch.from_numpy(kf.pose)).numpy())
-    assert np.array_equal(buf[22 * n + 32:].reshape(4, 4), np.linalg.inv(kf.pose))
+    buf = pack_keyframe(kf.tensor_cam, kf.R_cam, kf.scores, kf.pred_boxes, kf.pred_proj_xy, kf.pose, kf.K, kf.image_size, frame_id=7)
+    H = 56                                                     # BF_KF_HEADER (include/boxfusion_b200.h)
+    assert buf.dtype == np.float32 and buf.shape == (H + 22 * n,)
+    assert buf.view(np.int32)[0] == n and buf.view(np.int32)[1] == 7
+    assert np.array_equal(buf[2:8], np.array([kf.K[0, 0], kf.K[1, 1], kf.K[0, 2], kf.K[1, 2], kf.image_size[0], kf.image_size[1]], np.float32))
+    assert np.array_equal(buf[8:24].reshape(4, 4), kf.pose)
+    assert np.array_equal(buf[24:40].reshape(4, 4), torch.linalg.inv(torch.from_numpy(kf.pose)).numpy())
+    assert np.array_equal(buf[40:56].reshape(4, 4), np.linalg.inv(kf.pose))
+    assert np.array_equal(buf[H + 6 * n:H + 15 * n].reshape(n, 3, 3), kf.R_cam) and np.array_equal(buf[H + 15 * n:H + 16 * n], kf.scores)
     rec = replay.KeyframeRecorder()
     rec.add_keyframe(kf)
     rec.add(5, kf.pose, kf.K, kf.image_size, kf.tensor_cam, kf.R_cam, torch.from_numpy(kf.scores), kf.pred_boxes, kf.pred_proj_xy)
