@@ -14,7 +14,7 @@ import os
 import numpy as np
 import torch
 
-from . import ops
+from . import fastpath, ops
 
 
 def _load_pst(path) -> np.ndarray:
@@ -149,12 +149,39 @@ class BoxFusion(object):
         return mean, per_boxes_3d_R[best]
 
     # ---- the hot path (box_fusion.py:622-724) --------------------------------------------------------
+    def _enter_fast_path(self, all_pred_box, per_frame_box, box_manager):
+        """After an ordinary call: move the state into a FusionEngine so that the next keyframes of a demo.py-shaped caller
+        run on the engine (fastpath.py).  Purely an optimisation: on any failure the call-by-call path simply carries on."""
+        if not fastpath.ENABLED or box_manager._session is not None or box_manager._fast_strikes >= 3:
+            return
+        try:
+            if not fastpath.Session.importable(all_pred_box, per_frame_box, box_manager):
+                return
+            dev = all_pred_box.pred_boxes_3d.tensor.device
+            sess = box_manager._fast_engine
+            if sess is None or sess.dev != dev or sess.key != fastpath.cfg_key(self.cfg) or sess.engine.pst.shape[0] != self.PST.shape[0]:
+                sess = fastpath.Session(box_manager, self.cfg, dev)
+                box_manager._fast_engine = sess
+            sess.import_state(all_pred_box, per_frame_box, box_manager)
+            box_manager._session = sess
+            box_manager._fast_strikes += 1                        # a caller that keeps leaving the fast path stops entering it
+        except RuntimeError:
+            box_manager._session = None
+            box_manager._fast_strikes = 3
+
     def boxfusion(self, all_pred_box, per_frame_box, box_manager, beta=0.9, verbose=False):
+        sess = fastpath.session_of(box_manager)
+        if sess is not None:
+            if sess.try_boxfusion(self, all_pred_box, per_frame_box, box_manager, beta):
+                box_manager._fast_strikes = 0
+                return
+            sess.detach(box_manager)
         N_box = len(all_pred_box)
         fl = box_manager.fusion_list
         todo = [i for i in range(N_box) if len(fl[i]) >= 3 and not box_manager.check_if_fusion(fl[i])]
         self.last_iters = None
         if not todo:
+            self._enter_fast_path(all_pred_box, per_frame_box, box_manager)
             return
         boxes = per_frame_box.get("pred_boxes_3d")
         dev = ops._pick_device(boxes.tensor, all_pred_box.pred_boxes_3d.tensor)
@@ -193,3 +220,4 @@ class BoxFusion(object):
             idx = torch.as_tensor([todo[k] for k in rows], device=tgt.device)
             src = out[torch.as_tensor(rows, device=out.device)] if tgt.is_cuda else torch.from_numpy(out_h[rows])
             tgt[idx] = src.to(tgt.device)                                               # :721, in place
+        self._enter_fast_path(all_pred_box, per_frame_box, box_manager)

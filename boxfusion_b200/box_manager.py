@@ -26,10 +26,12 @@ from . import ops
 class BoxManager:
 
     def __init__(self, cfg):
-        self.fusion_list: List[List[int]] = []     # per map box: per-frame observation indices supporting it
+        self._session = None                        # fastpath.Session while the manager's state lives in a FusionEngine
+        self._fast_engine, self._fast_strikes = None, 0
+        self._fusion_list: List[List[int]] = []    # per map box: per-frame observation indices supporting it
         self.last_fusion_frame: List[List[int]] = []
-        self.fusion_flag: List[int] = []
-        self.already_fusion: List[List[int]] = []
+        self._fusion_flag: List[int] = []
+        self._already_fusion: List[List[int]] = []
         self._fused_set, self._fused_n = set(), 0
         self.num_record: Dict[int, int] = {}
         self.cfg = cfg
@@ -38,14 +40,52 @@ class BoxManager:
         self.small_size = self.cfg["box_fusion"]["small_size"]
         self.merge_log: List[Dict] = []
 
+    # ---- the public lists (box_manager.py:13-16).  While a fastpath.Session runs they live on the device and are downloaded
+    #      when somebody looks; assigning them, or any of the list-editing methods below, ends the session first ----------
+    def _lists(self, name):
+        if self._session is not None:
+            self._session.lists_for_caller(self)
+        return getattr(self, name)
+
+    def _leave_fast_path(self):
+        if self._session is not None:
+            self._session.detach(self)
+
+    fusion_list = property(lambda self: self._lists("_fusion_list"))
+    fusion_flag = property(lambda self: self._lists("_fusion_flag"))
+    already_fusion = property(lambda self: self._lists("_already_fusion"))
+
+    @fusion_list.setter
+    def fusion_list(self, v):
+        self._leave_fast_path()
+        self._fusion_list = v
+
+    @fusion_flag.setter
+    def fusion_flag(self, v):
+        self._leave_fast_path()
+        self._fusion_flag = v
+
+    @already_fusion.setter
+    def already_fusion(self, v):
+        self._leave_fast_path()
+        self._already_fusion = v
+
     # ---- bookkeeping (box_manager.py:24-38, 131-166) ---------------------------------------------
     def init_new_predictions(self, box_num, all_num):
+        s = self._session
+        if s is not None:
+            if s.stage in (s.IDLE, s.CORR) and int(all_num) == s.M + (s.n if s.stage == s.CORR else 0):
+                s.pending_new = (int(box_num), int(all_num))      # the engine creates these rows when the detections are ingested
+                s.lists_host = False
+                return
+            s.detach(self)
         for i in range(box_num):
             self.fusion_list.append([i + all_num])
             self.last_fusion_frame.append([0])
             self.fusion_flag.append(0)
 
     def add_fusion_ind(self, idx_list):
+        self._leave_fast_path()
         if self._fused_n == len(self.already_fusion):        # keep the lookup set in step with the public list
             self._fused_set.add(tuple(idx_list))
             self._fused_n += 1
@@ -60,9 +100,15 @@ class BoxManager:
         return tuple(idx_list) in self._fused_set
 
     def update(self, keep_idx):
+        s = self._session
+        if s is not None:
+            if s.stage == s.CORR and len(keep_idx) == s.N:
+                return                                            # the engine compacted the lists together with the map rows
+            s.detach(self)
         self.fusion_list = [self.fusion_list[i] for i in keep_idx]
 
     def update_fusion_flag(self, idx):
+        self._leave_fast_path()
         self.fusion_flag[idx] = 1
 
     def get_fusion_idx(self):
@@ -72,6 +118,12 @@ class BoxManager:
         return [i for i in range(len(self.fusion_flag)) if self.fusion_flag[i] == 0]
 
     def check_valid_num(self, all_pred_box, count, gap):
+        s = self._session
+        if s is not None:
+            fast = s.try_check_valid(self, all_pred_box, count, gap)
+            if fast is not None:
+                return fast
+            s.detach(self)
         zero = torch.where((all_pred_box.valid_num == 0) & (all_pred_box.frame_id < (count - gap)))[0]
         valid = torch.arange(len(all_pred_box))
         if zero.shape[0] > 0:
@@ -85,7 +137,7 @@ class BoxManager:
     def pack_lists(self, n: int):
         """fusion_list/fusion_flag of the first n boxes -> (list[n,CAP] i32, len[n] i32, flag[n] i32) numpy."""
         cap = ops.FUSION_CAP
-        lists = self.fusion_list[:n]
+        lists = self._fusion_list[:n]
         ln = np.fromiter(map(len, lists), dtype=np.int32, count=n)
         if n and ln.max() > cap:
             raise RuntimeError(f"a fusion list has {int(ln.max())} entries; device capacity is {cap}")
@@ -95,11 +147,12 @@ class BoxManager:
         rows = np.repeat(np.arange(n), ln)
         cols = np.arange(total) - np.repeat(np.cumsum(ln) - ln, ln)
         fl[rows, cols] = flat
-        flag = np.asarray(self.fusion_flag[:n], dtype=np.int32)
+        flag = np.asarray(self._fusion_flag[:n], dtype=np.int32)
         return fl, ln, flag
 
     def apply_lists(self, fl: np.ndarray, ln: np.ndarray, flag: np.ndarray, old_len: np.ndarray):
         """Write back rows the kernel changed (in place, like `fusion_list[cur] += ...; .sort()`)."""
+        self._leave_fast_path()
         for i in np.nonzero(ln != old_len)[0]:
             self.fusion_list[i][:] = [int(x) for x in fl[i, :ln[i]]]
         for i in np.nonzero(flag != np.asarray(self.fusion_flag[:len(flag)], dtype=np.int32))[0]:
@@ -129,6 +182,7 @@ class BoxManager:
 
     def record(self, cur_id, fusion_inds, init_id, cam_poses, box_size, keep, box_centers):
         """box_manager.py:40-88 (host replay; predicates from bf_pose_disparity)."""
+        self._leave_fast_path()
         fl = self.fusion_list
         for idx in fusion_inds:
             cdis = self.euclidean_distance_3d(box_centers[cur_id], box_centers[idx]) > 0.5
@@ -155,6 +209,7 @@ class BoxManager:
 
     def record_corr(self, cur_id, fusion_inds, init_id, cam_poses, keep):
         """box_manager.py:90-129 (host replay; predicates from bf_pose_disparity)."""
+        self._leave_fast_path()
         fl = self.fusion_list
         for idx in fusion_inds:
             if len(fl[idx]) == 1:

@@ -114,6 +114,16 @@ class EngineFields(dict):
         self.fill(); return dict.pop(self, *a)
 
 
+def cfg_key(cfg) -> tuple:
+    """Every cfg value the engine froze into its captured keyframe (a caller may edit the dict between keyframes)."""
+    bf, a = cfg["box_fusion"], cfg["association"]
+    ro = bf["random_opt"]
+    return (float(bf["nms_threshold"]), float(a["small_threshold"]), float(bf["small_size"]), float(a["translation_gap"]),
+            float(a["rotation_gap"]), bool(bf["use"]), bool(bf.get("check_valid")), int(cfg["data"]["gap"]), int(bf["iters"]),
+            int(bf["pst_size"]), float(ro["center_init_size"]), float(ro["center_scaling_coefficient"]),
+            float(ro["shape_init_size"]), float(ro["shape_scaling_coefficient"]))
+
+
 def _plain_fields(ins) -> dict:
     f = ins._fields
     if isinstance(f, EngineFields):
@@ -138,6 +148,9 @@ class Session:
         from .engine import FusionEngine
         from . import instances as inst_mod
         self.cfg = cfg
+        self.key = cfg_key(cfg)
+        self.use_fusion, self.check_valid, self.gap = bool(cfg["box_fusion"]["use"]), bool(cfg["box_fusion"].get("check_valid")), int(cfg["data"]["gap"])
+        self.map_dev, self.store_dev = {}, {}        # device of every engine-held field in the caller's own containers
         self.engine = FusionEngine(cfg, device=device, map_capacity=map_capacity, store_capacity=store_capacity,
                                    fused_capacity=fused_capacity, max_det=max_det, iou_mode=inst_mod.IOU_MODE)
         self.iou_mode = inst_mod.IOU_MODE
@@ -158,6 +171,8 @@ class Session:
         self.store_chunks = {}          # fields of per_frame_ins the engine does not hold: name -> list of per-keyframe values
         self.lists_host = True          # BoxManager's Python lists are current
         self.lists_given = None         # copies of the lists handed to the caller while the device is ahead
+        self.pending_new = None         # init_new_predictions(n, M) the engine has not seen yet
+        self.frame_id = -1
         self._keep = np.zeros(self.engine.ncap, dtype=np.int32)
         self._succ = np.zeros(self.engine.ncap, dtype=np.int32)
         self.image_size = None
@@ -170,6 +185,7 @@ class Session:
             e._check(rc, "bf_engine_step")
         ops.Profile.launches += sum(c for i, c in enumerate(e.launch_counts[:7]) if phases >> i & 1)
         e._state_fresh = False
+        self.lists_host = False                                    # fusion lists / flags / already_fusion move on the device
 
     def _read_flags(self, count, want_success):
         e = self.engine
@@ -194,7 +210,13 @@ class Session:
         """Fill an EngineFields with views of the engine state (same layout FusionEngine.export produces)."""
         from .boxes import GeneralInstance3DBoxes
         e = self.engine
-        put = lambda k, v: dict.__setitem__(f, k, v)       # noqa: E731
+        devs = self.store_dev if f.kind == "store" else self.map_dev
+
+        def put(k, v):
+            d = devs.get(k)
+            if d is not None and d.type == "cpu":          # the caller keeps this field on the host (demo.py:216-219): hand out a copy there
+                v = v.to(d) if isinstance(v, torch.Tensor) else v
+            dict.__setitem__(f, k, v)
         if f.kind == "store":
             M = f.rows
             st = e.store
@@ -276,6 +298,8 @@ class Session:
         self.N, self.M = N, M
         self.map_extras = {k: v for k, v in fa.items() if k not in _MAP_NATIVE}
         self.store_chunks = {k: [v] for k, v in fp.items() if k not in _STORE_NATIVE}
+        self.map_dev = {k: fa[k].device for k in _MAP_NATIVE if isinstance(fa[k], torch.Tensor)}
+        self.store_dev = {k: fp[k].device for k in _STORE_NATIVE if isinstance(fp[k], torch.Tensor)}
         self.image_size = A.image_size
         # the caller's own containers become views of the engine state (in-place edits stay coherent)
         for c, kind, rows in ((A, "map", N), (P, "store", M)):
@@ -320,6 +344,8 @@ class Session:
 
     def detach(self, bm):
         """Leave the fast path: everything the session holds becomes plain state again."""
+        if bm is None or bm._session is not self:
+            return
         e = self.engine
         edited = not self.lists_untouched(bm)
         if self.stage == Session.NMS:                              # the engine applies valid_num += 1 in its correspondence phase
@@ -329,8 +355,17 @@ class Session:
                     if e.stream is not None:
                         torch.cuda.current_stream(self.dev).wait_stream(e.stream)
                     e.map["valid"][torch.from_numpy(succ).to(self.dev)] += 1
+        if self.stage == Session.CORR:                             # close the keyframe on the device too (row counters)
+            self._phase(_lib.PH_FINISH)
+            self.M += self.n
+            self.stage = Session.IDLE
         if not edited and not self.lists_host:
             self.pull_lists(bm)
+        if self.stage == Session.IDLE and self.pending_new is not None:   # rows init_new_predictions announced, not yet ingested
+            n_new, m0 = self.pending_new
+            for i in range(n_new):
+                bm._fusion_list.append([i + m0]); bm.last_fusion_frame.append([0]); bm._fusion_flag.append(0)
+        self.pending_new = None
         e.state()                                                  # everything issued so far has completed
         for c in (self.map_c, self.store_c, self.cat_c):
             if c is not None and isinstance(c._fields, EngineFields):
@@ -390,8 +425,16 @@ class Session:
         K, H, W, pose = proj
         fid = fb["frame_id"]
         frame_id = int(fid[0]) if isinstance(fid, torch.Tensor) else int(np.asarray(fid).reshape(-1)[0])
-        from .engine import keyframe_header
-        hdr = keyframe_header(n, frame_id, K, (W, H), pose)
+        # header of the keyframe: n, frame id, intrinsics, pose, np.linalg.inv(pose) for the correspondence projection
+        # (instances.py:680); the observation projection was done by the caller's project_3d_boxes
+        pose = np.ascontiguousarray(pose.detach().cpu().numpy() if isinstance(pose, torch.Tensor) else pose, dtype=np.float32).reshape(4, 4)
+        hdr = np.zeros(KF_HEADER, dtype=np.float32)
+        hi = hdr.view(np.int32)
+        hi[0], hi[1] = n, frame_id
+        K3 = np.asarray(K, dtype=np.float32)
+        hdr[2:8] = (K3[0, 0], K3[1, 1], K3[0, 2], K3[1, 2], float(W), float(H))
+        hdr[8:24] = pose.reshape(-1)
+        hdr[40:56] = np.linalg.inv(pose).astype(np.float32).reshape(-1)
         st = e._st()
         if e.stream is not None:
             e.stream.wait_stream(torch.cuda.current_stream(self.dev))
@@ -404,6 +447,7 @@ class Session:
         ops.Profile.calls["bf_engine_ingest_world"] = ops.Profile.calls.get("bf_engine_ingest_world", 0) + 1
         e._state_fresh = False
         self.hdr, self.n, self.pred, self.frame_id = hdr, n, B, frame_id
+        self.pending_new = None
         self.cat_extras = {k: _cat_values(v, fb[k]) for k, v in self.map_extras.items()}
         self.stage = Session.CAT
         self.lists_host, self.lists_given = False, None
@@ -414,7 +458,7 @@ class Session:
         if A is not self.cat_c or self.stage != Session.CAT or bm._session is not self:
             return None
         from . import instances as inst_mod
-        if float(threshold) != float(self.cfg["box_fusion"]["nms_threshold"]) or inst_mod.IOU_MODE != self.iou_mode:
+        if float(threshold) != self.key[0] or inst_mod.IOU_MODE != self.iou_mode or cfg_key(self.cfg) != self.key:
             return None
         self._phase(_lib.PH_NMS)
         rows = self.N + self.n
@@ -445,9 +489,9 @@ class Session:
             return None
         K, Hh, Wh, _ = self.pred._bf_proj
         Ki = intrinsic.detach().cpu().numpy() if isinstance(intrinsic, torch.Tensor) else np.asarray(intrinsic)
-        if (float(threshold) != float(self.cfg["association"]["small_threshold"]) or float(H) != float(Hh) or float(W) != float(Wh)
+        if (float(threshold) != self.key[1] or float(H) != float(Hh) or float(W) != float(Wh)
                 or not np.array_equal(np.asarray(Ki, dtype=np.float32)[:3, :3], np.asarray(K, dtype=np.float32)[:3, :3])
-                or cfg["box_fusion"]["small_size"] != self.cfg["box_fusion"]["small_size"]
+                or cfg_key(cfg) != self.key
                 or not np.array_equal(np.asarray(mask), self.last_keep)):
             return None
         c, keep_idx = self._after_assoc(all_pred_box.image_size)
@@ -470,7 +514,7 @@ class Session:
 
     def try_check_valid(self, bm, all_pred_box, count, gap):
         if (all_pred_box is not self.map_c or self.stage != Session.CORR or bm._session is not self or self.map_extras
-                or not self.cfg["box_fusion"].get("check_valid") or int(gap) != int(self.cfg["data"]["gap"]) or int(count) != self.frame_id):
+                or not self.check_valid or int(gap) != self.gap or int(count) != self.frame_id):
             return None
         self._phase(_lib.PH_VALID)
         self.N = None                                             # known on the device only
@@ -479,7 +523,7 @@ class Session:
 
     def try_boxfusion(self, fuser, all_pred_box, per_frame_box, bm, beta):
         if (all_pred_box is not self.map_c or per_frame_box is not self.store_c or self.stage != Session.CORR or bm._session is not self
-                or beta != 0.9 or not fuser.early_stop or not self.cfg["box_fusion"]["use"]):
+                or beta != 0.9 or not fuser.early_stop or not self.use_fusion or cfg_key(fuser.cfg) != self.key):
             return None
         K, H, W, _ = self.pred._bf_proj
         if (float(fuser.H) != float(H) or float(fuser.W) != float(W)

@@ -21,7 +21,7 @@ from typing import Any, Dict, List, Tuple, Union
 import numpy as np
 import torch
 
-from . import ops
+from . import fastpath, ops
 
 IOU_MODE = ops.IOU_SAMPLED_REF
 
@@ -140,6 +140,8 @@ class Instances3D:
         return ret
 
     def __len__(self) -> int:
+        if isinstance(self._fields, fastpath.EngineFields) and not self._fields.filled:
+            return self._fields.n_rows()                 # a view of the engine state: the row count is known without touching it
         for v in self._fields.values():
             return v.shape[0] if isinstance(v, (torch.Tensor, np.ndarray)) else v.__len__()
         raise NotImplementedError("Empty Instances3D does not support __len__!")
@@ -148,6 +150,10 @@ class Instances3D:
         raise NotImplementedError("`Instances3D` object is not iterable!")
 
     def __getitem__(self, item: Union[int, slice, torch.Tensor, np.ndarray, list]) -> "Instances3D":
+        if isinstance(self._fields, fastpath.EngineFields) and fastpath.ENABLED:
+            fast = self._fields.sess.try_getitem(self, item)          # `all_pred_box[mask]` of demo.py:325 on the engine
+            if fast is not None:
+                return fast
         if type(item) == int:
             if item >= len(self) or item < -len(self):
                 raise IndexError("Instances3D index out of range!")
@@ -207,6 +213,13 @@ class Instances3D:
         assert len(instance_lists) > 0
         if len(instance_lists) == 1:
             return instance_lists[0]
+        sess = fastpath.find_session(*instance_lists)
+        if sess is not None:                                          # demo.py:253-254 on the engine: row copies, lazy views
+            fast = sess.try_cat(instance_lists)
+            if fast is not None:
+                return fast
+            if sess.bm() is not None:
+                sess.detach(sess.bm())
         ret = Instances3D(image_size=instance_lists[0]._image_size)
         for k in instance_lists[0]._fields.keys():
             values = [i.get(k) for i in instance_lists]
@@ -252,12 +265,19 @@ class Instances3D:
         K = _as_numpy(K)
         uv = ops.project_boxes(corners, pose_inv.to(dev), K, float(W), float(H))
         self.projected_boxes = uv if boxes.tensor.is_cuda else uv.to(boxes.tensor.device)
+        self._bf_proj = (K, H, W, cam_pose[0])              # what the engine-backed path (fastpath.py) needs to know about this keyframe
 
     def spatial_association(instance_lists, threshold, box_manager, cam_poses):
         """3-D NMS association of map + new detections (instances.py:372-397) -> (keep, success) sorted lists."""
         assert len(instance_lists) > 0
         if len(instance_lists) == 1:
             return instance_lists                              # reference quirk (:381-382), preserved
+        sess = fastpath.session_of(box_manager)
+        if sess is not None:
+            fast = sess.try_nms(instance_lists, threshold, box_manager)
+            if fast is not None:
+                return fast
+            sess.detach(box_manager)
         boxes = instance_lists.get("pred_boxes_3d")
         dev = ops._pick_device(boxes.tensor)
         corners, centers = ops.box_corners(boxes.tensor, boxes.R, want_centers=True)
@@ -269,10 +289,16 @@ class Instances3D:
                                    all_pred_box, all_poses, per_frame_ins_cam_pose, frame_id, mask, intrinsic,
                                    all_kf_pose, threshold=0.33, H=480, W=640):
         """2-D correspondence association for small objects (instances.py:411-490)."""
+        sess = fastpath.session_of(box_manager)
+        if sess is not None:
+            fast = sess.try_corr(cfg, box_manager, pred_instances, all_pred_box, all_poses, frame_id, mask, intrinsic, threshold, H, W)
+            if fast is not None:
+                return fast
+            sess.detach(box_manager)
         N_glo = len(global_pred_box)
         keep_idx = copy.deepcopy(np.asarray(mask))
         small_size = cfg["box_fusion"]["small_size"]
-        host = getattr(all_pred_box, "_bf_host", None)       # left by spatial_association's download, if any
+        host = all_pred_box.__dict__.pop("_bf_host", None)   # left by spatial_association's download for exactly this call
         if host is not None and host["n"] == len(all_pred_box):
             pred_max = host["max_dim"][N_glo:]
         else:
