@@ -105,10 +105,12 @@ PROTOTYPES = {
     "bf_engine_set_counts": (_i32, [_vp, _i32, _i32, _vp]),
     "bf_engine_read_state": (_i32, [_vp, _ESP, _vp]),
     "bf_engine_read_flags": (_i32, [_vp, _vp, _vp, _i32, _ESP, _vp]),
+    "bf_engine_read_i32": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "bf_engine_pointers": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "bf_engine_launch_counts": (_i32, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     "bf_detection_filter": (_i32, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _f64, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "bf_probe_fp32": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
+    "bf_probe_fp64": (_i32, [_vp, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f32)]),
     "bf_set_option": (_i32, [_vp, _i32, _i32]),
     "bf_refine_last_launch": (_i32, [_vp]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),

@@ -27,7 +27,7 @@ extern "C" int bf_create(int device, bf_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     { const char* t = getenv("BF_REFINE_TIMING"); h->refine_timing = (t && (t[0] == '1' || t[0] == '2')) ? (t[0] - '0') : 0; }
     { const char* t = getenv("BF_REFINE_PERSISTENT"); h->refine_force_persistent = t ? atoi(t) : 0; }
-    { const char* t = getenv("BF_REFINE_SHAPE"); h->refine_force_variant = -1; if (t) sscanf(t, "%d,%d,%d", &h->refine_force_c, &h->refine_force_t, &h->refine_force_variant); }
+    { const char* t = getenv("BF_REFINE_SHAPE"); h->refine_force_variant = -1; h->refine_force_mode = -1; if (t) sscanf(t, "%d,%d,%d,%d", &h->refine_force_c, &h->refine_force_t, &h->refine_force_variant, &h->refine_force_mode); }
     *out = h;
     return BF_OK;
 }
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) bf_fma_probe_kernel(float* __restrict__ o
 
 extern "C" int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host*/) {
     if (!h || iters < 1 || !tflops_out) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_probe_fp32", "bad argument");
+    bf_device_guard guard(h);
     const int blocks = h->sm_count * 8, threads = 256;
     void* p;
     int rc = bf_scratch(h, BF_SCRATCH_MISC, sizeof(float) * (size_t)blocks * threads, &p);
@@ -78,6 +79,48 @@ extern "C" int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*
     for (int r = 0; r < 5; ++r) {
         BF_CUDA(h, cudaEventRecord(e0));
         bf_fma_probe_kernel<<<blocks, threads>>>((float*)p, iters);
+        BF_CUDA(h, cudaEventRecord(e1));
+        BF_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        BF_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return BF_OK;
+}
+
+__global__ void __launch_bounds__(256) bf_dfma_probe_kernel(double* __restrict__ out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double b = 0.999, c = 0.001;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int bf_probe_fp64(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host*/) {
+    if (!h || iters < 1 || !tflops_out) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_probe_fp64", "bad argument");
+    bf_device_guard guard(h);
+    const int blocks = h->sm_count * 8, threads = 256;
+    void* p;
+    int rc = bf_scratch(h, BF_SCRATCH_MISC, sizeof(double) * (size_t)blocks * threads, &p);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    BF_CUDA(h, cudaEventCreate(&e0));
+    BF_CUDA(h, cudaEventCreate(&e1));
+    bf_dfma_probe_kernel<<<blocks, threads>>>((double*)p, iters);          // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        BF_CUDA(h, cudaEventRecord(e0));
+        bf_dfma_probe_kernel<<<blocks, threads>>>((double*)p, iters);
         BF_CUDA(h, cudaEventRecord(e1));
         BF_CUDA(h, cudaEventSynchronize(e1));
         float ms = 0.f;

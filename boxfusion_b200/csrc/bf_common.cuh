@@ -33,6 +33,7 @@ struct bf_handle {
     int last_refine_cluster;    // cluster size * 1000 + block size of the last bf_refine launch (diagnostic)
     int refine_occ[20];         // cached cudaOccupancyMaxActiveClusters answers per (cluster size, block size)
     long long refine_occ_smem[20];   // dynamic shared memory (+1) the cached answer was computed for
+    int refine_force_mode;      // 4th field of BF_REFINE_SHAPE: -1 = automatic, 0 = one (view, particle) term per thread pass, 1 = one thread per particle
     int refine_force_c, refine_force_t, refine_force_variant;   // BF_REFINE_SHAPE="C,T[,variant]" in the environment: force the launch shape / kernel instantiation (tuning sweeps)
     int refine_concurrent;      // BF_OPT_REFINE_CONCURRENT
     int refine_timing;          // BF_REFINE_TIMING=1 in the environment: bf_refine's trace carries per-iteration phase cycle counts (diagnostic)

@@ -820,6 +820,19 @@ extern "C" int bf_engine_read_flags(bf_engine* e, int32_t* keep, int32_t* succes
     return BF_OK;
 }
 
+// diagnostic read-back of engine-owned per-keyframe results: which = 0 refine iterations per box, 1 CSR view offsets,
+// 2 rows selected for refinement, 3 refine `updated` flags (synchronises)
+extern "C" int bf_engine_read_i32(bf_engine* e, int which, int32_t* out, int count, void* stream) {
+    if (!e || !out || count < 0 || count > e->cfg.map_capacity + 1) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_read_i32", "bad argument");
+    bf_device_guard guard(e->h);
+    const int32_t* src = which == 0 ? e->its : which == 1 ? e->offsets : which == 2 ? e->todo : which == 3 ? e->upd : nullptr;
+    if (!src) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_read_i32", "bad selector");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count) E_CUDA(e, cudaMemcpyAsync(out, src, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    E_CUDA(e, cudaStreamSynchronize(st));
+    return BF_OK;
+}
+
 extern "C" int bf_engine_pointers(bf_engine* e, int32_t** keep, int32_t** success, bf_engine_state** state_dev, int32_t** refine_iters,
                                   int32_t** todo) {
     if (!e) return BF_ERR_INVALID_ARG;

@@ -116,7 +116,7 @@ extern __shared__ __align__(16) unsigned char bf_refine_smem_raw[];
 //                    L1.5 instruction cache; `no_instruction` was the second largest stall), 64 registers, four CTAs per SM.
 template <bool ROLL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int pst_cap, int force_mode_b, int timing) {
+bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int pst_cap, int force_mode_b, int fit_dist, int timing) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks();
     const unsigned crank = cluster.block_rank();
@@ -134,16 +134,19 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
     bf_refine_smem* sm = (bf_refine_smem*)bf_refine_smem_raw;
     bf_refine_state* S = &sm->S;
     bf_view* views = (bf_view*)(sm + 1);
-    float* fit = (float*)(views + max_views);              // [2][P]
-    int* cnt = (int*)(fit + 2 * P);                        // per (round, warp) hit counts -> exclusive prefixes (+ total)
+    const int n_eval = min(32 * (cfg.pst_size / 32), P);
+    int PB = (n_eval + (int)C - 1) / (int)C;
+    PB = (PB + 31) & ~31;                                // a warp never straddles two views
+    // fitness vector, double-buffered: a full copy [2][P] in every CTA (latency regime: the selection reads local shared
+    // memory), or - fit_dist, throughput regime - only the CTA's own block [2][PB], read by the other CTAs through DSMEM
+    // (shared memory is worth more as L1 for the polygon buffers there, and the selection is a vanishing share of an iteration)
+    const int fit_len = fit_dist ? PB : P;
+    float* fit = (float*)(views + max_views);
+    int* cnt = (int*)(fit + 2 * fit_len);                  // per (round, warp) hit counts -> exclusive prefixes (+ total)
     float* terms = (float*)(cnt + BF_CNT_SLOTS);           // [8][max_hits] addends of cal_transform
     float* spst = terms + 8 * cfg.max_hits;                // particle template staged in shared memory when it fits (pst_cap = P)
     float* contrib = spst + 6 * pst_cap;                   // [V][PB] terms of this CTA's particle block (mode A)
     if (cid >= B) return;                                // cluster-uniform: nothing to do (before any barrier)
-
-    const int n_eval = min(32 * (cfg.pst_size / 32), P);
-    int PB = (n_eval + (int)C - 1) / (int)C;
-    PB = (PB + 31) & ~31;                                // a warp never straddles two views
     const int p_lo = (int)crank * PB;
     const float beta = (float)cfg.beta, omb = (float)(1.0 - cfg.beta);
     const int nw = T >> 5, lane = tid & 31, warp = tid >> 5;
@@ -209,8 +212,14 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
         for (int n = 0; n < cfg.iters; ++n) {
             long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
             if (timing) tc0 = clock64();
-            float* fitb = fit + (git & 1u) * P;
+            float* fitb = fit + (git & 1u) * fit_len;
             ++git;
+            // fitness of particle j as the selection sees it
+            auto fit_at = [&](int j) -> float {
+                if (!fit_dist) return fitb[j];
+                const int r = j / PB;
+                return cluster.map_shared_rank(fitb, r)[j - r * PB];
+            };
             // ---- evaluate_iou (:413-461) for this CTA's particle block ----
             if (!mode_b) {
                 const int items = PB * V;
@@ -235,7 +244,8 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
                     const int p = p_lo + lp;
                     if (p < n_eval) {
                         const float f = bf_sum_views<4>(contrib + lp, PB, V) / denom;
-                        for (unsigned r = 0; r < C; ++r) cluster.map_shared_rank(fitb, r)[p] = f;
+                        if (fit_dist) fitb[lp] = f;
+                        else for (unsigned r = 0; r < C; ++r) cluster.map_shared_rank(fitb, r)[p] = f;
                     }
                 }
             } else {
@@ -252,7 +262,8 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
                         for (int v = 0; v < V; ++v)
                             value += bf_eval_view<ROLL>(c, views[v], cfg.fx, cfg.cx, cfg.fy, cfg.cy, cfg.img_w, cfg.img_h, &overflow, nullptr);
                         const float f = value / denom;
-                        for (unsigned r = 0; r < C; ++r) cluster.map_shared_rank(fitb, r)[p] = f;
+                        if (fit_dist) fitb[lp] = f;
+                        else for (unsigned r = 0; r < C; ++r) cluster.map_shared_rank(fitb, r)[p] = f;
                     }
                 }
                 if (timing) {
@@ -267,11 +278,11 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
             //      j >= 1 with fit[j] < fit[0] in index order.  Particle j = r*T + tid; its rank among the hits = hits of
             //      earlier (round, warp) groups + hits of lower lanes.  Pass 1: per-group ballot counts; warp 0 turns the
             //      counts into exclusive prefixes; pass 2: ranks and the eight addends of every selected particle.
-            const float origin = (n_eval >= 1) ? fitb[0] : unlaunched;
+            const float origin = (n_eval >= 1) ? fit_at(0) : unlaunched;
 #pragma unroll 1
             for (int r = 0; r < rounds; ++r) {
                 const int j = r * T + tid;
-                const float f = (j < n_eval) ? fitb[j] : unlaunched;
+                const float f = (j < n_eval) ? fit_at(j) : unlaunched;
                 const bool hit = (j >= 1 && j < P) && (f < origin);
                 const unsigned bal = __ballot_sync(0xffffffffu, hit);
                 if (lane == 0) cnt[r * nw + warp] = __popc(bal);
@@ -297,7 +308,7 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
             for (int r = 0; r < rounds; ++r) {
                 if (cnt[r * nw] >= cfg.max_hits) break;             // block-uniform: every later rank is beyond the cap
                 const int j = r * T + tid;
-                const float f = (j < n_eval) ? fitb[j] : unlaunched;
+                const float f = (j < n_eval) ? fit_at(j) : unlaunched;
                 const bool hit = (j >= 1 && j < P) && (f < origin);
                 const unsigned bal = __ballot_sync(0xffffffffu, hit);
                 const int pos = cnt[r * nw + warp] + __popc(bal & ((1u << lane) - 1u));
@@ -406,12 +417,13 @@ bf_refine_kernel(const bf_refine_params prm, int contrib_cap, int max_views, int
         }
     }
     if (overflow) atomicExch(prm.status, BF_ERR_CAPACITY);
+    if (fit_dist && C > 1) cluster.sync();               // nobody reads this CTA's fitness block any more
 }
 
 #define BF_CONTRIB_CAP 8192    // (view, particle) terms a CTA holds in shared memory in mode A: 32 KB
 
-static size_t bf_refine_smem_bytes(int P, int max_hits, int contrib_cap, int max_views, int pst_cap) {
-    return sizeof(bf_refine_smem) + sizeof(bf_view) * (size_t)max_views + sizeof(float) * 2 * (size_t)P +
+static size_t bf_refine_smem_bytes(int fit_len, int max_hits, int contrib_cap, int max_views, int pst_cap) {
+    return sizeof(bf_refine_smem) + sizeof(bf_view) * (size_t)max_views + sizeof(float) * 2 * (size_t)fit_len +
            sizeof(int) * (size_t)BF_CNT_SLOTS + sizeof(float) * 8 * (size_t)max_hits + sizeof(float) * (size_t)contrib_cap + sizeof(float) * 6 * (size_t)pst_cap + 16;
 }
 
@@ -420,7 +432,7 @@ static int bf_particle_block(int n_eval, int C) {
     return (PB + 31) & ~31;
 }
 
-typedef void (*bf_refine_fn)(const bf_refine_params, int, int, int, int, int);
+typedef void (*bf_refine_fn)(const bf_refine_params, int, int, int, int, int, int);
 
 static int bf_refine_occupancy(bf_handle* h, bf_refine_fn kern, int variant, int ci, int ti, int C, int T, size_t smem, cudaStream_t st) {
     const int slot = ci * 4 + ti;
@@ -469,9 +481,9 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
         variant = ((double)B * (double)items >= (double)h->sm_count * 8192.0) ? 2 : 1;
         bestT = 256;
         const long long slots = (long long)h->sm_count * (variant == 2 ? 4 : 3);
-        while (bestC < 16 && (long long)B * bestC * 2 <= slots + slots / 8) bestC *= 2;           // fill the resident CTA slots once
-        // one thread per particle with the views in a register once every thread has several evaluations anyway
-        mode_b = ((long long)bf_particle_block(n_eval, bestC) * avg_views >= 4LL * bestT) ? 1 : 0;
+        // about two waves of CTAs: boxes that stop early leave their slots to the second wave (measured on C4, round 2:
+        // clusters of 2 / 4 / 8 / 16 -> 74 / 63 / 59 / 62 ms forced, 46 / 34 / 31 / 30 ms with early stop)
+        while (bestC < 16 && (long long)B * bestC * 2 <= 2 * slots) bestC *= 2;
         best_cost = 0.0;
     }
     if (!saturated && !persistent && h->refine_concurrent) {       // BF_OPT_REFINE_CONCURRENT: leave room for the other streams' kernels
@@ -484,6 +496,9 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
         variant = (h->refine_force_variant >= 0 && h->refine_force_variant < 3) ? h->refine_force_variant : variant;
         if (h->refine_force_t <= kernel_max_t[variant]) { bestC = h->refine_force_c; bestT = h->refine_force_t; best_cost = 0.0; }
     }
+    // one thread per particle with the views in a register once every thread has several evaluations anyway
+    if (saturated) mode_b = ((long long)bf_particle_block(n_eval, bestC) * avg_views >= 4LL * bestT) ? 1 : 0;
+    if (h->refine_force_mode >= 0) mode_b = h->refine_force_mode;
     const bf_refine_fn kern = kernels[variant];
     // the particle template itself in shared memory when it is small (24 KB at P = 1024) - latency regime only: it shortens
     // the selection, but in the throughput regimes the space is worth more as resident CTAs and L1
@@ -495,7 +510,8 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
     };
     int contrib_cap = contrib_for(best_cost > 0.0 ? 1 : bestC);
     // rounded up to 8 KB so that the cached occupancy answers below are reused across keyframes
-    size_t smem = bf_refine_smem_bytes(P, cfg->max_hits, contrib_cap, max_views, pst_cap);
+    const int fit_dist = (saturated && mode_b && bestC > 1) ? 1 : 0;
+    size_t smem = bf_refine_smem_bytes(fit_dist ? bf_particle_block(n_eval, bestC) : P, cfg->max_hits, contrib_cap, max_views, pst_cap);
     smem = (variant == 0) ? (smem + 8191) / 8192 * 8192 : (smem + 1023) / 1024 * 1024;
     BF_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BF_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -527,7 +543,7 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = bestC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&lc, kern, prm, contrib_cap, max_views, pst_cap, mode_b, h->refine_timing);
+        cudaError_t e = cudaLaunchKernelEx(&lc, kern, prm, contrib_cap, max_views, pst_cap, mode_b, fit_dist, h->refine_timing);
         if (e != cudaSuccess) return bf_fail(h, BF_ERR_CUDA, "bf_refine_kernel", cudaGetErrorString(e));
         h->last_refine_cluster = variant * 1000000 + bestC * 1000 + bestT;
     }

@@ -169,6 +169,21 @@ class FusionEngine:
         s = self.state()
         return {"B": int(s.B), "views": int(s.SV)}
 
+    def refine_evals(self, B: int) -> int:
+        """(particle, view) evaluations of the last keyframe's refinement: sum over its boxes of iterations x views x
+        evaluated particles (reads the engine's per-box iteration counts; measurement passes only)."""
+        if B <= 0:
+            return 0
+        p_its, p_off = ctypes.c_void_p(), ctypes.c_void_p()
+        self.lib.bf_engine_pointers(self.e, None, None, None, ctypes.byref(p_its), None)
+        its = np.zeros(B, dtype=np.int32)
+        off = np.zeros(B + 1, dtype=np.int32)
+        self._check(self.lib.bf_engine_read_i32(self.e, 0, its.ctypes.data, B, self._st()), "bf_engine_read_i32")
+        self._check(self.lib.bf_engine_read_i32(self.e, 1, off.ctypes.data, B + 1, self._st()), "bf_engine_read_i32")
+        P = int(self.pst.shape[0])
+        n_eval = min(32 * (int(self.cfg["box_fusion"]["pst_size"]) // 32), P)
+        return int(np.sum(its.astype(np.int64) * np.diff(off).astype(np.int64)) * n_eval)
+
     def reset(self) -> None:
         """Start a new sequence in the same buffers (and with the same scratch and graphs)."""
         self._check(self.lib.bf_engine_reset(self.e, self._st()), "bf_engine_reset")

@@ -296,6 +296,15 @@ def probe_fp32(iters: int = 4096, device=None) -> float:
     return float(tf.value)
 
 
+def probe_fp64(iters: int = 2048, device=None) -> float:
+    """Measured FP64 FMA throughput (TFLOP/s) of the device: denominator of the sampled-IoU roofline."""
+    h = handle(_dev(device))
+    tf = ctypes.c_double(0.0)
+    ms = ctypes.c_float(0.0)
+    h.check(h.lib.bf_probe_fp64(h.h, int(iters), ctypes.byref(tf), ctypes.byref(ms)), "bf_probe_fp64")
+    return float(tf.value)
+
+
 def detection_filter(xyzlhw, proj_xy, scores, W: float, H: float, score_thresh: float, uv_ratio: Optional[float] = None,
                      floor_ratio: Optional[float] = None, size_max: Optional[float] = None):
     """demo.py:138-148 in one kernel: (keep[n] bool, flags[n] int32: bit0 score, bit1 uv bounds, bit2 floor, bit3 large)."""

@@ -289,6 +289,9 @@ int bf_engine_read_state(bf_engine* e, bf_engine_state* out /*host*/, void* stre
  * synchronisation (any pointer may be NULL). */
 int bf_engine_read_flags(bf_engine* e, int32_t* keep /*host*/, int32_t* success /*host*/, int count, bf_engine_state* state /*host*/,
                          void* stream);
+/* Diagnostic read-back (synchronises) of engine-owned per-keyframe results: which = 0 refine iterations per box,
+ * 1 CSR view offsets of the refined boxes, 2 map rows selected for refinement, 3 their `updated` flags. */
+int bf_engine_read_i32(bf_engine* e, int which, int32_t* out /*host*/, int count, void* stream);
 /* Device pointers of engine-owned per-keyframe results (valid for the engine's lifetime). */
 int bf_engine_pointers(bf_engine* e, int32_t** keep, int32_t** success, bf_engine_state** state_dev, int32_t** refine_iters,
                        int32_t** todo);
@@ -306,6 +309,8 @@ int bf_detection_filter(bf_handle* h, const float* xyzlhw /*[n,6]*/, const float
 /* Diagnostic: measured FP32 FMA throughput (TFLOP/s) of the device - the denominator of the FP32-pipe
  * roofline bench.py reports.  Synchronous; outputs are HOST pointers. */
 int bf_probe_fp32(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host or NULL*/);
+/* The same for the FP64 pipe (the sampled IoU's plane tests are float64): denominator of the `iou` block's roofline. */
+int bf_probe_fp64(bf_handle* h, int iters, double* tflops_out /*host*/, float* ms_out /*host or NULL*/);
 
 #ifdef __cplusplus
 }
