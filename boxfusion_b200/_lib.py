@@ -57,7 +57,7 @@ class EngineCfg(ctypes.Structure):
                 ("translation_gap", _f32), ("rotation_gap", _f32), ("center_gap", _f32),
                 ("small_size", _f32), ("small_plus", _f32),
                 ("use_fusion", ctypes.c_int32), ("check_valid", ctypes.c_int32), ("gap", ctypes.c_int32), ("use_graph", ctypes.c_int32),
-                ("refine", RefineCfg), ("pst", _vp), ("P", ctypes.c_int32)]
+                ("concurrent", ctypes.c_int32), ("refine", RefineCfg), ("pst", _vp), ("P", ctypes.c_int32)]
 
 
 class EngineBuffers(ctypes.Structure):
@@ -86,6 +86,8 @@ PROTOTYPES = {
     "bf_box_corners": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bf_transform2world": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "bf_project_boxes": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "bf_transform2world_pose": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "bf_project_boxes_pose": (_i32, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "bf_iou3d_matrix": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bf_nms3d": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f32, _f32, _f32, _i32,
                         _vp, _vp, _vp, _vp]),

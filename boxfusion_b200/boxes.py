@@ -76,7 +76,11 @@ class GeneralInstance3DBoxes(object):
             return
         if self.tensor.is_cuda:
             t, r = self.tensor.contiguous(), self.R.contiguous()
-            ops.transform2world_(t, r, cam_pose)
+            one = ops.shared_pose(cam_pose) if cam_pose.shape[0] == t.shape[0] else None
+            if one is not None:                                  # demo.py:216: one pose for the keyframe's detections
+                ops.transform2world_pose_(t, r.view(-1, 9) if r.dim() == 3 else r, one)
+            else:
+                ops.transform2world_(t, r, cam_pose)
             self.tensor, self.R = t, r
         else:
             dev = ops._dev()

@@ -13,11 +13,11 @@ __global__ void bf_rank_kernel(const int32_t* __restrict__ order, const bf_dimre
 }
 
 // ---- score order of nms_3d (instances.py:52) ---------------------------------------------------------------------
-// 64-bit keys (descending score, ascending index), unique per box.  N <= 4096: block 0 sorts them ascending with a
-// bitonic network in shared memory.  Larger N (the 4 352-box stress map of BASELINE configs[2], engine maps up to
+// 64-bit keys (descending score, ascending index), unique per box.  N <= 8192 (incl. the 4 352-box stress map of BASELINE
+// configs[2]): block 0 sorts them ascending with a bitonic network in shared memory.  Larger N (engine maps up to
 // 65 536 rows): every block ranks its boxes by counting the smaller keys, tile by tile through shared memory -
 // O(N^2) compares like the pair stage of the NMS it feeds, no multi-pass global sort, fixed launch shape.
-#define BF_ORDER_SMEM 4096
+#define BF_ORDER_SMEM 8192
 __device__ __forceinline__ unsigned long long bf_score_key(float f, int i) {
     unsigned u;
     if (f != f) u = 0xffffffffu;                                // NaN: greater than everything (torch's order)
@@ -31,7 +31,7 @@ __device__ __forceinline__ unsigned long long bf_score_key(float f, int i) {
 
 __global__ void __launch_bounds__(1024)
 bf_score_order_kernel(const float* __restrict__ scores, const bf_dimref Nd, int32_t* __restrict__ order, int32_t* __restrict__ rank) {
-    __shared__ unsigned long long bf_keys[BF_ORDER_SMEM];
+    extern __shared__ unsigned long long bf_keys[];      // BF_ORDER_SMEM keys (64 KB)
     const int N = bf_dim(Nd);
     if (N <= BF_ORDER_SMEM) {
         if (blockIdx.x != 0 || N <= 0) return;
@@ -76,7 +76,9 @@ bf_score_order_kernel(const float* __restrict__ scores, const bf_dimref Nd, int3
 
 int bf_score_order_run(bf_handle* h, const float* scores, bf_dimref Nd, int32_t* order, int32_t* rank, cudaStream_t st) {
     const int blocks = Nd.host <= BF_ORDER_SMEM ? 1 : (bf_blocks(Nd.host, 1024) < h->sm_count ? bf_blocks(Nd.host, 1024) : h->sm_count);
-    bf_score_order_kernel<<<blocks, 1024, 0, st>>>(scores, Nd, order, rank);
+    const size_t smem = sizeof(unsigned long long) * BF_ORDER_SMEM;
+    BF_CUDA(h, cudaFuncSetAttribute(bf_score_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bf_score_order_kernel<<<blocks, 1024, smem, st>>>(scores, Nd, order, rank);
     BF_LAUNCH_CHECK(h, "bf_score_order_kernel");
     return BF_OK;
 }
@@ -110,134 +112,116 @@ __device__ __forceinline__ void bf_record_head(const bf_record_ctx& ctx, const u
     if (any) { success[cur] = 1; ctx.flen[cur] = len_c; }
 }
 
-// Sparse greedy matching (the common case: few over-threshold pairs).  The IoU kernels emit one edge
-// (rank_lo << 32 | rank_hi) per over-threshold pair.  One CTA sorts the edges, thread 0 walks them in order to
-// decide which (head, partner) pairs are live - nms_3d's loop (instances.py:58-97) touches nothing else - and then
-// record() runs in parallel over heads: calls of different heads write disjoint lists/flags and only read lists of
-// suppressed boxes, which never change.  Falls through (returns) when the edge list overflowed; the dense kernel
-// below handles that case.  status is sticky (never cleared here): the caller zeroes it.
+// Greedy matching.  The IoU kernels emit one edge (rank_lo << 32 | rank_hi) per over-threshold pair (and set the pair's
+// bit in the dense rank-space mask when there is one).  One CTA.
+//   sparse path (the common case, <= BF_EDGE_CAP edges): sort the edges in shared memory, thread 0 walks them in order to
+//     decide which (head, partner) pairs are live - nms_3d's loop (instances.py:58-97) touches nothing else;
+//   dense path (edge list overflowed): the mask read row by row IS the sorted edge list.  Warp 0 walks, in ascending score
+//     rank, the heads that have at least one over-threshold partner and writes the LIVE (head, partner) pairs - at most one
+//     per box, a box is suppressed once - to `live`;
+// then record() runs in parallel over heads in both cases: calls of different heads write disjoint lists/flags and only read
+// lists of suppressed boxes, which never change.  status is sticky (never cleared here): the caller zeroes it.
 #define BF_EDGE_CAP 8192
 __global__ void __launch_bounds__(1024)
-bf_greedy_edges_kernel(const unsigned long long* __restrict__ edges, const unsigned long long* __restrict__ counters,
-                       const bf_dimref Nd, int have_dense, bf_record_ctx ctx, int32_t* __restrict__ success) {
+bf_greedy_kernel(const unsigned long long* __restrict__ edges, const unsigned long long* __restrict__ counters,
+                 const bf_dimref Nd, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ rowany,
+                 unsigned long long* __restrict__ live, bf_record_ctx ctx, int32_t* __restrict__ success) {
     extern __shared__ unsigned long long s_keys[];
+    __shared__ int s_E;
     const int N = bf_dim(Nd);
     const int W = (N + 31) >> 5;
     const unsigned long long E64 = counters[6];
-    const int tid = threadIdx.x, T = blockDim.x;
-    if (E64 > BF_EDGE_CAP) {
-        if (!have_dense && tid == 0) atomicExch(ctx.status, BF_ERR_CAPACITY);   // no dense mask for maps this large
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    if (tid == 0 && counters[5]) atomicExch(ctx.status, BF_ERR_CAPACITY);       // the IoU stage's candidate list overflowed (fixed-size scratch)
+    const bool dense = E64 > BF_EDGE_CAP;
+    if (dense && !mask) {
+        if (tid == 0) atomicExch(ctx.status, BF_ERR_CAPACITY);                   // no dense mask for maps this large
         return;
     }
-    const int E = (int)E64;
+    const int E_sparse = dense ? 0 : (int)E64;
     int n2 = 1;
-    while (n2 < E) n2 <<= 1;
-    uint32_t* remaining = (uint32_t*)(s_keys + n2);
+    while (n2 < E_sparse) n2 <<= 1;
+    // shared memory: [sorted keys (sparse path only)] [remaining bit set] [live flags (sparse path only)]
+    uint32_t* remaining = (uint32_t*)(s_keys + (dense ? 0 : n2));
     unsigned char* act = (unsigned char*)(remaining + W);
     for (int i = tid; i < N; i += T) { ctx.keep[i] = 0; success[i] = 0; }
-    for (int i = tid; i < n2; i += T) s_keys[i] = (i < E) ? edges[i] : ~0ULL;
     for (int w = tid; w < W; w += T) {
         const int base = w << 5;
         remaining[w] = (base + 32 <= N) ? 0xffffffffu : ((base < N) ? ((1u << (N - base)) - 1u) : 0u);
     }
-    __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1)                      // bitonic sort, ascending
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n2; i += T) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const unsigned long long a = s_keys[i], b = s_keys[p];
-                    if (((i & k) == 0) ? (a > b) : (a < b)) { s_keys[i] = b; s_keys[p] = a; }
+    const unsigned long long* keys;
+    const unsigned char* actp;
+    int E;
+    if (!dense) {
+        for (int i = tid; i < n2; i += T) s_keys[i] = (i < E_sparse) ? edges[i] : ~0ULL;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)                      // bitonic sort, ascending
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n2; i += T) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const unsigned long long a = s_keys[i], b = s_keys[p];
+                        if (((i & k) == 0) ? (a > b) : (a < b)) { s_keys[i] = b; s_keys[p] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid == 0) {                                        // the serial part of nms_3d: who is a head, who is suppressed
+            int cur = -1;
+            bool alive = false;
+            for (int e = 0; e < E_sparse; ++e) {
+                const int r0 = (int)(s_keys[e] >> 32), r1 = (int)(s_keys[e] & 0xffffffffu);
+                if (r0 != cur) { cur = r0; alive = (remaining[r0 >> 5] >> (r0 & 31)) & 1u; }
+                const bool lv = alive && ((remaining[r1 >> 5] >> (r1 & 31)) & 1u);
+                act[e] = lv ? 1 : 0;
+                if (lv) remaining[r1 >> 5] &= ~(1u << (r1 & 31));
+            }
+        }
+        __syncthreads();
+        keys = s_keys; actp = act; E = E_sparse;
+    } else {
+        __syncthreads();
+        if (tid < 32) {
+            int En = 0;
+            for (int hw = 0; hw < W; ++hw) {
+                uint32_t heads = rowany[hw];
+                while (heads) {
+                    const int bit = __ffs(heads) - 1;
+                    heads &= heads - 1;
+                    const int r = (hw << 5) + bit;
+                    if (!((remaining[hw] >> bit) & 1u)) continue;                  // suppressed earlier: never a head
+                    for (int w0 = 0; w0 < W; w0 += 32) {                            // partners in ascending rank = descending score (:85)
+                        const int w = w0 + lane;
+                        const uint32_t sb = (w < W) ? (mask[(size_t)r * W + w] & remaining[w]) : 0u;
+                        const int cpop = __popc(sb);
+                        int incl = cpop;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                        int pos = En + incl - cpop;
+                        uint32_t q = sb;
+                        while (q) {
+                            const int b2 = __ffs(q) - 1;
+                            q &= q - 1;
+                            live[pos++] = ((unsigned long long)r << 32) | (unsigned long long)((w << 5) + b2);
+                        }
+                        if (w < W) remaining[w] &= ~sb;
+                        En += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    __syncwarp();
                 }
             }
-            __syncthreads();
+            if (lane == 0) s_E = En;
         }
-    if (tid == 0) {                                        // the serial part of nms_3d: who is a head, who is suppressed
-        int cur = -1;
-        bool alive = false;
-        for (int e = 0; e < E; ++e) {
-            const int r0 = (int)(s_keys[e] >> 32), r1 = (int)(s_keys[e] & 0xffffffffu);
-            if (r0 != cur) { cur = r0; alive = (remaining[r0 >> 5] >> (r0 & 31)) & 1u; }
-            const bool live = alive && ((remaining[r1 >> 5] >> (r1 & 31)) & 1u);
-            act[e] = live ? 1 : 0;
-            if (live) remaining[r1 >> 5] &= ~(1u << (r1 & 31));
-        }
+        __threadfence_block();
+        __syncthreads();
+        keys = live; actp = nullptr; E = s_E;
     }
-    __syncthreads();
     for (int e = tid; e < E; e += T) {                     // one thread per head: record() over its live partners, in order
-        if (e > 0 && (int)(s_keys[e - 1] >> 32) == (int)(s_keys[e] >> 32)) continue;
-        bf_record_head(ctx, s_keys, act, e, E, success);
+        if (e > 0 && (int)(keys[e - 1] >> 32) == (int)(keys[e] >> 32)) continue;
+        bf_record_head(ctx, keys, actp, e, E, success);
     }
     __syncthreads();
     for (int r = tid; r < N; r += T) {                     // keep = never suppressed, minus dropped heads, plus forced keeps
-        const int i = ctx.order[r];
-        const bool rem = (remaining[r >> 5] >> (r & 31)) & 1u;
-        const int k = ctx.keep[i];
-        ctx.keep[i] = (k == 1) ? 1 : ((k == -1) ? 0 : (rem ? 1 : 0));
-    }
-}
-
-// Dense fallback (edge list overflowed): the rank-space bit mask read row by row IS the sorted edge list.  Warp 0 walks,
-// in ascending score rank, the heads that have at least one over-threshold partner (every other box is kept untouched)
-// and writes the LIVE (head, partner) pairs - at most one per box, a box is suppressed once - to `live`; then record()
-// runs in parallel over heads exactly as in the sparse kernel.
-__global__ void __launch_bounds__(1024)
-bf_greedy_dense_kernel(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ rowany, const bf_dimref Nd,
-                       bf_record_ctx ctx, int32_t* __restrict__ success, const unsigned long long* __restrict__ counters,
-                       unsigned long long* __restrict__ live) {
-    extern __shared__ uint32_t s_mem[];
-    if (counters[6] <= BF_EDGE_CAP) return;              // bf_greedy_edges_kernel handled this call
-    const int N = bf_dim(Nd);
-    const int W = (N + 31) >> 5;
-    uint32_t* remaining = s_mem;            // [W] ranks not yet suppressed
-    __shared__ int s_E;
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
-    for (int w = tid; w < W; w += T) {
-        const int base = w << 5;
-        remaining[w] = (base + 32 <= N) ? 0xffffffffu : ((base < N) ? ((1u << (N - base)) - 1u) : 0u);
-    }
-    for (int i = tid; i < N; i += T) { ctx.keep[i] = 0; success[i] = 0; }
-    __syncthreads();
-    if (tid < 32) {
-        int E = 0;
-        for (int hw = 0; hw < W; ++hw) {
-            uint32_t heads = rowany[hw];
-            while (heads) {
-                const int bit = __ffs(heads) - 1;
-                heads &= heads - 1;
-                const int r = (hw << 5) + bit;
-                if (!((remaining[hw] >> bit) & 1u)) continue;                  // suppressed earlier: never a head
-                for (int w0 = 0; w0 < W; w0 += 32) {                            // partners in ascending rank = descending score (:85)
-                    const int w = w0 + lane;
-                    const uint32_t s = (w < W) ? (mask[(size_t)r * W + w] & remaining[w]) : 0u;
-                    const int c = __popc(s);
-                    int incl = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-                    int pos = E + incl - c;
-                    uint32_t q = s;
-                    while (q) {
-                        const int b2 = __ffs(q) - 1;
-                        q &= q - 1;
-                        live[pos++] = ((unsigned long long)r << 32) | (unsigned long long)((w << 5) + b2);
-                    }
-                    if (w < W) remaining[w] &= ~s;
-                    E += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                __syncwarp();
-            }
-        }
-        if (lane == 0) s_E = E;
-    }
-    __syncthreads();
-    const int E = s_E;
-    __threadfence_block();
-    for (int e = tid; e < E; e += T) {
-        if (e > 0 && (int)(live[e - 1] >> 32) == (int)(live[e] >> 32)) continue;
-        bf_record_head(ctx, live, nullptr, e, E, success);
-    }
-    __syncthreads();
-    for (int r = tid; r < N; r += T) {
         const int i = ctx.order[r];
         const bool rem = (remaining[r >> 5] >> (r & 31)) & 1u;
         const int k = ctx.keep[i];
@@ -298,17 +282,11 @@ int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_di
     ctx.order = order; ctx.init_id = init_id; ctx.poses = poses; ctx.centers = centers; ctx.fl = fusion_list;
     ctx.flen = fusion_len; ctx.fflag = fusion_flag; ctx.keep = keep; ctx.status = status;
     ctx.translation_gap = translation_gap; ctx.rotation_gap = rotation_gap_deg; ctx.center_gap = center_gap;
-    // sparse path: sorted edge list in shared memory (keys + remaining bit set + live flags)
+    // sorted edge list in shared memory (keys + remaining bit set + live flags); the dense path needs the bit set only
     const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
-    BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-    bf_greedy_edges_kernel<<<1, 1024, smem_e, st>>>(edges, counters, Nd, dense ? 1 : 0, ctx, success);
-    BF_LAUNCH_CHECK(h, "bf_greedy_edges_kernel");
-    if (dense) {
-        // dense fallback: returns immediately unless the edge list overflowed
-        const size_t smem = sizeof(uint32_t) * (size_t)W + 16;
-        bf_greedy_dense_kernel<<<1, 1024, smem, st>>>(mask, rowany, Nd, ctx, success, counters, live);
-        BF_LAUNCH_CHECK(h, "bf_greedy_dense_kernel");
-    }
+    BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    bf_greedy_kernel<<<1, 1024, smem_e, st>>>(edges, counters, Nd, dense ? mask : nullptr, rowany, live, ctx, success);
+    BF_LAUNCH_CHECK(h, "bf_greedy_kernel");
     return BF_OK;
 }
 

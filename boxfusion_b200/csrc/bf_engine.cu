@@ -405,12 +405,16 @@ __device__ __forceinline__ bool e_in_fused(const bf_fused_table& ft, int F, cons
 }
 
 // which map boxes are refined this keyframe (box_fusion.py:631-635) -> todo[], CSR offsets / view_index;
-// st->B, st->SV, st->maxV.  One CTA.
+// st->B, st->SV, st->maxV.  One CTA.  The "view set fused before?" test (BoxManager.check_if_fusion, box_manager.py:34-38)
+// walks the already_fusion hashes in shared-memory tiles: every thread compares its candidate rows against the whole
+// tile, only hash hits touch the lists themselves.
+#define BF_ESEL_TILE 2048
 __global__ void __launch_bounds__(BF_ESCAN_THREADS)
 bf_engine_select_kernel(bf_engine_ctx c) {
     __shared__ int s_w[BF_ESCAN_THREADS / 32];
     __shared__ int s_wv[BF_ESCAN_THREADS / 32];
     __shared__ int s_maxv;
+    __shared__ unsigned long long s_hash[BF_ESEL_TILE];
     bf_engine_state* st = c.st;
     const bf_map_buffers& mp = c.map[0];
     const bf_fused_table& ft = c.fused;
@@ -422,14 +426,39 @@ bf_engine_select_kernel(bf_engine_ctx c) {
     const int per = (N + BF_ESCAN_THREADS - 1) / BF_ESCAN_THREADS;
     const int lo = min(N, tid * per), hi = min(N, lo + per);
     int cnt = 0, vsum = 0, vmax = 0;
-    unsigned long long picks = 0ull;                          // per <= 64 rows per thread (N <= 65536)
-    for (int i = lo; i < hi && active; ++i) {
-        const int len = mp.flen[i];
-        if (len < 3) continue;
-        const int32_t* l = mp.fl + (size_t)i * BF_FUSION_CAP;
-        if (e_in_fused(ft, F, l, len, e_list_hash(l, len))) continue;
-        if (len > BF_MAX_VIEWS) { st->status[5] = BF_ERR_CAPACITY; continue; }
-        if (i - lo < 64) picks |= 1ull << (i - lo);
+    unsigned long long picks = 0ull;                          // per <= 64 rows per thread (N <= 65536): candidates, then survivors
+    if (active)
+        for (int i = lo; i < hi; ++i) {
+            const int len = mp.flen[i];
+            if (len < 3) continue;
+            if (len > BF_MAX_VIEWS) { st->status[5] = BF_ERR_CAPACITY; continue; }
+            picks |= 1ull << (i - lo);
+        }
+    if (active)
+        for (int f0 = 0; f0 < F; f0 += BF_ESEL_TILE) {        // block-uniform trip count
+            const int nf = min(BF_ESEL_TILE, F - f0);
+            __syncthreads();
+            for (int f = tid; f < nf; f += BF_ESCAN_THREADS) s_hash[f] = ft.hash[f0 + f];
+            __syncthreads();
+            unsigned long long rest = picks;
+            while (rest) {
+                const int k = __ffsll((long long)rest) - 1;
+                rest &= rest - 1;
+                const int i = lo + k;
+                const int len = mp.flen[i];
+                const int32_t* l = mp.fl + (size_t)i * BF_FUSION_CAP;
+                const unsigned long long h = e_list_hash(l, len);
+                for (int f = 0; f < nf; ++f) {
+                    if (s_hash[f] != h || ft.len[f0 + f] != len) continue;
+                    const int32_t* q = ft.lists + (size_t)(f0 + f) * BF_FUSION_CAP;
+                    bool same = true;
+                    for (int j = 0; j < len; ++j) same &= (q[j] == l[j]);
+                    if (same) { picks &= ~(1ull << k); break; }
+                }
+            }
+        }
+    for (unsigned long long rest = picks; rest; rest &= rest - 1) {
+        const int len = mp.flen[lo + __ffsll((long long)rest) - 1];
         ++cnt; vsum += len; vmax = max(vmax, len);
     }
     int incl = cnt, vincl = vsum;
@@ -464,25 +493,39 @@ bf_engine_select_kernel(bf_engine_ctx c) {
         const int B = s_w[BF_ESCAN_THREADS / 32 - 1], SV = s_wv[BF_ESCAN_THREADS / 32 - 1];
         c.offsets[B] = SV;
         st->B = B; st->SV = SV; st->maxV = s_maxv;
+        st->pad[2] = F;                                       // already_fusion entries before this keyframe's write-back
         st->refine_boxes_total += B; st->refine_views_total += SV;
     }
 }
 
-// write back fused boxes (box_fusion.py:716-724), sequentially in map order like the reference's loop
-__global__ void bf_engine_apply_kernel(bf_engine_ctx c) {
+// write back fused boxes (box_fusion.py:716-724), sequentially in map order like the reference's loop.  The rows in todo[]
+// were not in already_fusion when they were selected; a row can only have been fused "earlier in this very call"
+// (check_if_fusion at :634 runs inside the reference's loop) by one of the entries this call appended, so only those
+// are compared.  `finish` != 0: also close the keyframe (bf_engine_finish_kernel's work; one launch less in the
+// whole-keyframe graph).
+__global__ void bf_engine_apply_kernel(bf_engine_ctx c, int finish) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     bf_engine_state* st = c.st;
     const bf_map_buffers& mp = c.map[0];
     const bf_fused_table& ft = c.fused;
     const int B = st->B;
-    int F = ft.count[0];
+    const int F0 = ft.count[0];
+    int F = F0;
     for (int k = 0; k < B; ++k) {
+        if (!c.upd[k]) continue;
         const int i = c.todo[k];
         const int len = mp.flen[i];
         const int32_t* l = mp.fl + (size_t)i * BF_FUSION_CAP;
         const unsigned long long h = e_list_hash(l, len);
-        if (e_in_fused(ft, F, l, len, h)) continue;           // fused earlier in this very call (check_if_fusion, :634)
-        if (!c.upd[k]) continue;
+        bool dup = false;
+        for (int f = F0; f < F && !dup; ++f) {
+            if (ft.hash[f] != h || ft.len[f] != len) continue;
+            const int32_t* q = ft.lists + (size_t)f * BF_FUSION_CAP;
+            bool same = true;
+            for (int j = 0; j < len; ++j) same &= (q[j] == l[j]);
+            dup = same;
+        }
+        if (dup) continue;                                    // fused earlier in this very call (check_if_fusion, :634)
         for (int q = 0; q < 6; ++q) mp.tensor[6 * (size_t)i + q] = c.out[6 * (size_t)k + q];
         c.fflag[i] = 1;
         if (F >= ft.cap) { st->status[3] = BF_ERR_CAPACITY; continue; }
@@ -491,6 +534,7 @@ __global__ void bf_engine_apply_kernel(bf_engine_ctx c) {
         ++F;
     }
     ft.count[0] = F;
+    if (finish) { st->N = st->Nnew; st->M = st->M + st->n; st->steps += 1; st->n = 0; }
 }
 
 // close the keyframe: the counters the next keyframe starts from
@@ -502,10 +546,6 @@ __global__ void bf_engine_finish_kernel(bf_engine_ctx c) {
     st->n = 0;
 }
 
-// copies the IoU stage's overflow flag into the sticky status (the work list is fixed-size inside a graph)
-__global__ void bf_engine_nms_status_kernel(bf_engine_ctx c, const unsigned long long* __restrict__ counters) {
-    if (counters[5]) c.st->status[6] = BF_ERR_CAPACITY;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 static bf_engine_ctx e_ctx(const bf_engine* e) {
@@ -555,10 +595,9 @@ static int e_ph_nms(bf_engine* e, cudaStream_t st, int* L) {
     E_SUB(e, bf_nms3d_run(h, e->corners, e->centers, Nd, e->order, e->rank, mp.init_id, e->bufs.store.pose, mp.fl, mp.flen,
                           e->bufs.fusion_flag, g.nms_threshold, g.translation_gap, g.rotation_gap, g.center_gap, g.iou_mode,
                           e->keep, e->success, &e->state->status[0], st));
-    bf_engine_nms_status_kernel<<<1, 1, 0, st>>>(c, (const unsigned long long*)h->buf[BF_SCRATCH_COUNTERS]);
-    E_LAUNCH_CHECK(e, "bf_engine_nms_status_kernel");
-    // corners, order, planes, pairs, count, greedy (sparse), greedy (dense, if the map is small enough), status
-    *L = 7 + (g.map_capacity <= 16384 ? 1 : 0);
+    (void)c;
+    // corners, order, planes, pairs, count, greedy
+    *L = 6;
     return BF_OK;
 }
 
@@ -588,7 +627,7 @@ static int e_ph_compact(bf_engine* e, cudaStream_t st, int* L) { return e_compac
 static int e_ph_valid(bf_engine* e, cudaStream_t st, int* L) { return e_compaction(e, st, 1, L); }
 
 // BoxFusion.boxfusion (demo.py:304-305): selection, refinement, write-back
-static int e_ph_fuse(bf_engine* e, cudaStream_t st, int* L) {
+static int e_fuse(bf_engine* e, cudaStream_t st, int finish, int* L) {
     const bf_engine_ctx c = e_ctx(e);
     const bf_engine_cfg& g = e->cfg;
     bf_engine_select_kernel<<<1, BF_ESCAN_THREADS, 0, st>>>(c);
@@ -600,11 +639,12 @@ static int e_ph_fuse(bf_engine* e, cudaStream_t st, int* L) {
     const bf_store_buffers& sb = e->bufs.store;
     E_SUB(e, bf_refine_run(e->h, g.pst, g.P, sb.tensor, sb.R, sb.scores, sb.uv, sb.pose, e->offsets, e->view_index,
                            g.map_capacity, &rc, e->out, e->upd, e->its, nullptr, &e->state->status[2], &dv, st));
-    bf_engine_apply_kernel<<<1, 32, 0, st>>>(c);
+    bf_engine_apply_kernel<<<1, 32, 0, st>>>(c, finish);
     E_LAUNCH_CHECK(e, "bf_engine_apply_kernel");
     *L = 3;
     return BF_OK;
 }
+static int e_ph_fuse(bf_engine* e, cudaStream_t st, int* L) { return e_fuse(e, st, 0, L); }
 
 static int e_ph_finish(bf_engine* e, cudaStream_t st, int* L) {
     const bf_engine_ctx c = e_ctx(e);
@@ -619,10 +659,11 @@ static const e_phase_fn e_phases[PH_COUNT] = {e_ph_ingest, e_ph_nms, e_ph_corr, 
 
 static int e_issue(bf_engine* e, int phases, cudaStream_t st, int* launches) {
     int total = 0;
+    const bool fused_finish = (phases & (1 << PH_FUSE)) && (phases & (1 << PH_FINISH));   // bf_engine_apply closes the keyframe itself
     for (int p = 0; p < PH_COUNT; ++p) {
-        if (!(phases & (1 << p))) continue;
+        if (!(phases & (1 << p)) || (p == PH_FINISH && fused_finish)) continue;
         int L = 0;
-        const int rc = e_phases[p](e, st, &L);
+        const int rc = (p == PH_FUSE && fused_finish) ? e_fuse(e, st, 1, &L) : e_phases[p](e, st, &L);
         if (rc) return rc;
         total += L;
     }
@@ -678,6 +719,7 @@ extern "C" int bf_engine_create(int device, const bf_engine_cfg* cfg, const bf_e
     if (rc) { free(e); return rc; }
     bf_device_guard guard(e->h);
     e->cfg = *cfg; e->bufs = *bufs;
+    e->h->refine_concurrent = cfg->concurrent ? 1 : 0;
     const size_t ncap = (size_t)cfg->map_capacity;
     e->in_floats = BF_KF_HEADER + (size_t)BF_KF_ROW * cfg->max_det;
 #define E_ALLOC(ptr, bytes) do { cudaError_t ce = cudaMalloc((void**)&(ptr), (bytes)); if (ce != cudaSuccess) { bf_engine_destroy(e); return BF_ERR_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
@@ -709,10 +751,11 @@ extern "C" int bf_engine_create(int device, const bf_engine_cfg* cfg, const bf_e
         e->have_graph = 1;
     } else {
         // launch counts of the eager sequences (same kernels)
-        e->launches[PH_INGEST] = 1; e->launches[PH_NMS] = 7 + (cfg->map_capacity <= 16384 ? 1 : 0); e->launches[PH_CORR] = 1;
+        e->launches[PH_INGEST] = 1; e->launches[PH_NMS] = 6; e->launches[PH_CORR] = 1;
         e->launches[PH_COMPACT] = 3; e->launches[PH_VALID] = 3; e->launches[PH_FUSE] = 3; e->launches[PH_FINISH] = 1;
         int tot = 0;
         for (int p = 0; p < PH_COUNT; ++p) if (e_full_mask(e) & (1 << p)) tot += e->launches[p];
+        if (cfg->use_fusion) tot -= 1;                       // apply closes the keyframe itself
         e->launches[PH_COUNT] = tot;
     }
     return BF_OK;

@@ -120,6 +120,76 @@ extern "C" int bf_project_boxes(bf_handle* h, const float* corners, const float*
     return BF_OK;
 }
 
+// The two calls demo.py:220-221 makes per keyframe - transform2world(cam_pose) and project_3d_boxes(K, H, W) - when every
+// detection of the keyframe carries the same camera pose (it always does there: the pose is np.repeat-ed): the pose
+// travels as a kernel parameter (no host->device copy of [n,16] floats) and corners + projection are one kernel.
+// Same arithmetic, in the same order, as bf_transform2world_kernel / bf_corners_kernel / bf_project_kernel.
+struct bf_pose16 { float m[16]; };
+
+__global__ void bf_transform2world_pose_kernel(float* __restrict__ xyzlhw, float* __restrict__ R, const bf_pose16 pose, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* p = pose.m;
+    float* t = xyzlhw + 6 * n;
+    float* r = R + 9 * n;
+    const float c0 = t[0], c1 = t[1], c2 = t[2];
+    float rb[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rb[k] = r[k];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a0 = p[4 * i], a1 = p[4 * i + 1], a2 = p[4 * i + 2];
+        t[i] = __fadd_rn(dot3_seq(a0, c0, a1, c1, a2, c2), p[4 * i + 3]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[3 * i + j] = dot3_seq(a0, rb[j], a1, rb[3 + j], a2, rb[6 + j]);
+    }
+}
+
+extern "C" int bf_transform2world_pose(bf_handle* h, float* xyzlhw, float* R, const float* pose_host, int N, void* stream) {
+    bf_device_guard guard(h);
+    if (!h || N < 0 || !pose_host || (N > 0 && (!xyzlhw || !R))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_transform2world_pose", "bad argument");
+    if (N == 0) return BF_OK;
+    bf_pose16 p;
+    memcpy(p.m, pose_host, sizeof(p.m));
+    bf_transform2world_pose_kernel<<<bf_blocks(N, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, R, p, N);
+    BF_LAUNCH_CHECK(h, "bf_transform2world_pose_kernel");
+    return BF_OK;
+}
+
+__global__ void bf_project_boxes_pose_kernel(const float* __restrict__ xyzlhw, const float* __restrict__ R, int N, const bf_pose16 pinv,
+                                             float fx, float fy, float cx, float cy, float W, float H, float* __restrict__ uv) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * 8) return;
+    const int n = idx >> 3, v = idx & 7;
+    const float* t = xyzlhw + 6 * n;
+    const float* r = R + 9 * n;
+    const float hl = t[3] * 0.5f, hh = t[4] * 0.5f, hw = t[5] * 0.5f;
+    const float vx = ((v & 1) ^ ((v >> 1) & 1)) ? hl : -hl, vy = (v & 2) ? hh : -hh, vz = (v & 4) ? hw : -hw;
+    const float x = __fadd_rn(dot3_seq(r[0], vx, r[1], vy, r[2], vz), t[0]);
+    const float y = __fadd_rn(dot3_seq(r[3], vx, r[4], vy, r[5], vz), t[1]);
+    const float z = __fadd_rn(dot3_seq(r[6], vx, r[7], vy, r[8], vz), t[2]);
+    const float* p = pinv.m;
+    const float X = __fadd_rn(dot3_seq(p[0], x, p[1], y, p[2], z), p[3]);
+    const float Y = __fadd_rn(dot3_seq(p[4], x, p[5], y, p[6], z), p[7]);
+    const float Z = __fadd_rn(dot3_seq(p[8], x, p[9], y, p[10], z), p[11]);
+    float u = __fadd_rn(__fdiv_rn(__fmul_rn(fx, X), Z), cx);
+    float w = __fadd_rn(__fdiv_rn(__fmul_rn(fy, Y), Z), cy);
+    uv[2 * idx] = fminf(fmaxf(u, 0.f), W);
+    uv[2 * idx + 1] = fminf(fmaxf(w, 0.f), H);
+}
+
+extern "C" int bf_project_boxes_pose(bf_handle* h, const float* xyzlhw, const float* R, int N, const float* pose_inv_host, float fx,
+                                     float fy, float cx, float cy, float W, float H, float* uv, void* stream) {
+    bf_device_guard guard(h);
+    if (!h || N < 0 || !pose_inv_host || (N > 0 && (!xyzlhw || !R || !uv))) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_project_boxes_pose", "bad argument");
+    if (N == 0) return BF_OK;
+    bf_pose16 p;
+    memcpy(p.m, pose_inv_host, sizeof(p.m));
+    bf_project_boxes_pose_kernel<<<bf_blocks(8LL * N, 128), 128, 0, (cudaStream_t)stream>>>(xyzlhw, R, N, p, fx, fy, cx, cy, W, H, uv);
+    BF_LAUNCH_CHECK(h, "bf_project_boxes_pose_kernel");
+    return BF_OK;
+}
+
 // box_manager.py:168-186
 __global__ void bf_pose_disparity_kernel(const float* __restrict__ poses, const int32_t* __restrict__ ia,
                                          const int32_t* __restrict__ ib, int n, float* __restrict__ baseline,

@@ -183,7 +183,7 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
 
 // ------------------------------------------------------------------------------------------------
 // One CTA per candidate pair (persistent, CTA-stride over the work list): gate, then counts.
-#define BF_COUNT_THREADS 128
+#define BF_COUNT_THREADS 640     // 625 grid rows: one per thread (a keyframe has a few dozen candidate pairs: latency, not throughput)
 __global__ void __launch_bounds__(BF_COUNT_THREADS)
 bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA, const double* __restrict__ planesA,
                 const float* __restrict__ cornersB, const float* __restrict__ aabbB, const double* __restrict__ planesB,
@@ -205,10 +205,10 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
         __syncthreads();
         if (tid < 48) { s_pl[0][tid] = planesA[48 * (size_t)a + tid]; s_pl[1][tid] = planesB[48 * (size_t)b + tid]; }
         if (tid >= 64 && tid < 88) { s_c[0][tid - 64] = cornersA[24 * (size_t)a + tid - 64]; s_c[1][tid - 64] = cornersB[24 * (size_t)b + tid - 64]; }
-        if (tid >= 96 && tid < 96 + 3) {
-            const int ax = tid - 96;
+        if (tid >= 96 && tid < 96 + 3 * BF_NS) {
+            const int ax = (tid - 96) / BF_NS, i = (tid - 96) - ax * BF_NS;
             const float lo = fminf(aabbA[6 * a + ax], aabbB[6 * b + ax]), hi = fmaxf(aabbA[6 * a + 3 + ax], aabbB[6 * b + 3 + ax]);   // instances.py:581-582
-            for (int i = 0; i < BF_NS; ++i) s_grid[ax][i] = (double)bf_linspace25(lo, hi, i);
+            s_grid[ax][i] = (double)bf_linspace25(lo, hi, i);
         }
         __syncthreads();
         // ---- containment gate (instances.py:514-557): 2 x 20 points, one per thread -------------------------
@@ -316,7 +316,7 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float*
                                                      iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, edges, edge_cap);
     }
     BF_LAUNCH_CHECK(h, "bf_pairs_kernel");
-    const int grid = h->sm_count * 8;
+    const int grid = h->sm_count * 3;
     bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, Nd, work, (int)cap, counters,
                                                        iou, counts, thr, rank, mask, rowany, edges, edge_cap);
     BF_LAUNCH_CHECK(h, "bf_count_kernel");

@@ -491,7 +491,16 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
         while (bestC > 1 && (long long)bf_particle_block(n_eval, bestC / 2) * max_views <= bestT) bestC /= 2;
         best_cost = 0.0;
     }
-    if (persistent) { variant = 0; bestC = 16; bestT = 512; best_cost = 0.0; }
+    if (persistent) {
+        // one fixed shape for the captured engine step.  Latency shape: 16 x 512 threads, one CTA per SM.  With
+        // BF_OPT_REFINE_CONCURRENT (many engines share the GPU, bench.py c5): 16 x 256 threads of the 80-register
+        // instantiation, three CTAs per SM, so that the idle phases of one sequence's clusters (cluster barrier, selection)
+        // are filled by another sequence's evaluations.
+        variant = h->refine_concurrent ? 1 : 0; bestT = h->refine_concurrent ? 256 : 512; best_cost = 0.0;
+        // cluster size: 64 particles per CTA (8 views fill 512 threads in one pass); smaller templates leave room for more clusters
+        bestC = 1;
+        while (bestC < 16 && bestC * 64 < n_eval) bestC *= 2;
+    }
     if (h->refine_force_c > 0 && h->refine_force_t > 0) {          // BF_REFINE_SHAPE (tuning sweeps)
         variant = (h->refine_force_variant >= 0 && h->refine_force_variant < 3) ? h->refine_force_variant : variant;
         if (h->refine_force_t <= kernel_max_t[variant]) { bestC = h->refine_force_c; bestT = h->refine_force_t; best_cost = 0.0; }
@@ -529,7 +538,10 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
         }
     if (persistent) {
         // as many clusters as the machine holds at once, every cluster loops over boxes cluster_id, cluster_id + G, ...
-        int active = bf_refine_occupancy(h, kern, variant, 0, 0, bestC, bestT, smem, st);
+        int ci = 0;
+        while (ci < 4 && Cs[ci] != bestC) ++ci;
+        int active = bf_refine_occupancy(h, kern, variant, ci, h->refine_concurrent ? 2 : 0, bestC, bestT, smem, st);
+        if (h->refine_concurrent && active > 8) active = 8;   // a keyframe refines a handful of boxes; the rest of the machine is other engines'
         if (h->refine_force_persistent > 0 && h->refine_force_persistent < active) active = h->refine_force_persistent;
         if (active < 1) return bf_fail(h, BF_ERR_CUDA, "bf_refine", "no resident cluster for the persistent launch shape");
         clusters = active;

@@ -27,7 +27,10 @@ from .synthetic import Keyframe
 class FusionSession:
     """State that demo.py:run() keeps across keyframes (demo.py:72-83)."""
 
-    def __init__(self, impl, cfg: dict, device: str = "cpu", quiet: bool = True):
+    def __init__(self, impl, cfg: dict, device: str = "cpu", quiet: bool = True, frame_stride: int = 1):
+        """frame_stride: how far demo.py's frame counter `count` advances between two keyframes (cfg data.gap there: the
+        detector runs on every gap-th frame, demo.py:134-136, 200); frame ids and check_valid_num's `count - gap` are in frames."""
+        self.frame_stride = int(frame_stride)
         self.impl = impl
         self.cfg = cfg
         self.device = torch.device(device)
@@ -98,7 +101,7 @@ class FusionSession:
             n = kf.tensor_cam.shape[0]
             if n == 0:                                                          # demo.py:206-212
                 bm.num_record[count] = self.box_count
-                self.count += 1
+                self.count += self.frame_stride
                 return None
             pred_instances, pose_np = self.make_pred_instances(kf)
         self.box_count += len(pred_instances)
@@ -140,7 +143,7 @@ class FusionSession:
                 bm.update(keep_idx)
             self.all_pred_box, self.all_poses = all_pred_box, all_poses
         self.last_keep_idx = None if keep_idx is None else np.asarray(keep_idx).copy()
-        self.count += 1
+        self.count += self.frame_stride
         return self.last_keep_idx
 
     # snapshot of everything the API mutates, for parity comparison -----------

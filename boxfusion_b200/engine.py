@@ -63,7 +63,7 @@ def pack_keyframe(tensor_cam, R_cam, scores, pred_boxes, pred_proj_xy, pose, K=N
 class FusionEngine:
     def __init__(self, cfg: dict, device="cuda", map_capacity: int = 4096, store_capacity: int = 65536,
                  fused_capacity: int = 32768, iou_mode: int = ops.IOU_SAMPLED_REF, private_stream: bool = False,
-                 max_det: int = 128, use_graph: bool = True):
+                 max_det: int = 128, use_graph: bool = True, concurrent: Optional[bool] = None):
         """private_stream=True gives the engine its own CUDA stream, so that several engines - independent sequences - can be
         driven concurrently from one host thread (bench.py --workload c5); every engine has its own scratch in any case."""
         self.cfg = cfg
@@ -104,6 +104,7 @@ class FusionEngine:
         ec.small_size, ec.small_plus = float(np.float32(bf["small_size"])), float(np.float32(bf["small_size"] + 0.1))
         ec.use_fusion, ec.check_valid = int(bool(bf["use"])), int(bool(bf.get("check_valid")))
         ec.gap, ec.use_graph = int(cfg["data"]["gap"]), int(bool(use_graph))
+        ec.concurrent = int(private_stream if concurrent is None else bool(concurrent))
         ec.refine = ops.make_refine_cfg(cfg, self.K16.reshape(-1), self.H, self.W)
         ec.pst, ec.P = self.pst.data_ptr(), int(self.pst.shape[0])
         self._ec, self._bufs = ec, bufs
@@ -174,8 +175,6 @@ class FusionEngine:
         evaluated particles (reads the engine's per-box iteration counts; measurement passes only)."""
         if B <= 0:
             return 0
-        p_its, p_off = ctypes.c_void_p(), ctypes.c_void_p()
-        self.lib.bf_engine_pointers(self.e, None, None, None, ctypes.byref(p_its), None)
         its = np.zeros(B, dtype=np.int32)
         off = np.zeros(B + 1, dtype=np.int32)
         self._check(self.lib.bf_engine_read_i32(self.e, 0, its.ctypes.data, B, self._st()), "bf_engine_read_i32")
@@ -187,7 +186,7 @@ class FusionEngine:
     def reset(self) -> None:
         """Start a new sequence in the same buffers (and with the same scratch and graphs)."""
         self._check(self.lib.bf_engine_reset(self.e, self._st()), "bf_engine_reset")
-        self._state = EngineState()
+        ctypes.memset(ctypes.byref(self._state), 0, ctypes.sizeof(EngineState))
         self._state_fresh = True
         self.M = self.count = self._n_ub = 0
 

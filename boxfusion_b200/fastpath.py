@@ -64,16 +64,26 @@ def _index_values(v, idx: np.ndarray):
 
 
 class EngineFields(dict):
-    """`Instances3D._fields` whose values are views of the engine's buffers, created on first use."""
+    """`Instances3D._fields` whose values are views of the engine's buffers, each created when it is first asked for."""
 
-    def __init__(self, sess: "Session", kind: str, rows: Optional[int]):
+    def __init__(self, sess: "Session", kind: str, rows: Optional[int], names):
         super().__init__()
-        self.sess, self.kind, self.rows, self.filled = sess, kind, rows, False
+        self.sess, self.kind, self.rows = sess, kind, rows
+        self.pending = set(names)                  # fields not materialised yet
+
+    @property
+    def filled(self) -> bool:
+        return not self.pending
+
+    def _make(self, k):
+        self.pending.discard(k)
+        v = self.sess.view(self, k)
+        dict.__setitem__(self, k, v)
+        return v
 
     def fill(self):
-        if not self.filled:
-            self.filled = True
-            self.sess.materialize(self)
+        for k in list(self.pending):
+            self._make(k)
 
     def n_rows(self) -> int:
         if self.rows is None:
@@ -81,22 +91,27 @@ class EngineFields(dict):
         return self.rows
 
     def __getitem__(self, k):
-        self.fill(); return dict.__getitem__(self, k)
+        if k in self.pending:
+            return self._make(k)
+        return dict.__getitem__(self, k)
 
     def __setitem__(self, k, v):
-        self.fill(); dict.__setitem__(self, k, v)
+        self.pending.discard(k); dict.__setitem__(self, k, v)
 
     def __delitem__(self, k):
-        self.fill(); dict.__delitem__(self, k)
+        if k in self.pending:
+            self.pending.discard(k)
+        else:
+            dict.__delitem__(self, k)
 
     def __contains__(self, k):
-        self.fill(); return dict.__contains__(self, k)
+        return k in self.pending or dict.__contains__(self, k)
 
     def __iter__(self):
         self.fill(); return dict.__iter__(self)
 
     def __len__(self):
-        self.fill(); return dict.__len__(self)
+        return len(self.pending) + dict.__len__(self)
 
     def keys(self):
         self.fill(); return dict.keys(self)
@@ -108,10 +123,13 @@ class EngineFields(dict):
         self.fill(); return dict.items(self)
 
     def get(self, k, default=None):
-        self.fill(); return dict.get(self, k, default)
+        return self[k] if k in self else default
 
-    def pop(self, *a):
-        self.fill(); return dict.pop(self, *a)
+    def pop(self, k, *a):
+        if k in self.pending:
+            self.pending.discard(k)
+            return self.sess.view(self, k)
+        return dict.pop(self, k, *a)
 
 
 def cfg_key(cfg) -> tuple:
@@ -175,12 +193,15 @@ class Session:
         self.frame_id = -1
         self._keep = np.zeros(self.engine.ncap, dtype=np.int32)
         self._succ = np.zeros(self.engine.ncap, dtype=np.int32)
+        self._keep_p, self._succ_p = self._keep.ctypes.data, self._succ.ctypes.data
+        self._state_ref = ctypes.byref(self.engine._state)
+        self._stp = self.engine._st()   # stream of the keyframe in flight (looked up once per keyframe)
         self.image_size = None
 
     # ---- helpers ----------------------------------------------------------------------------------------------
     def _phase(self, phases):
         e = self.engine
-        rc = e.lib.bf_engine_step(e.e, None, self.n, phases, e._st())
+        rc = e.lib.bf_engine_step(e.e, None, self.n, phases, self._stp)
         if rc:
             e._check(rc, "bf_engine_step")
         ops.Profile.launches += sum(c for i, c in enumerate(e.launch_counts[:7]) if phases >> i & 1)
@@ -189,8 +210,7 @@ class Session:
 
     def _read_flags(self, count, want_success):
         e = self.engine
-        rc = e.lib.bf_engine_read_flags(e.e, self._keep.ctypes.data, self._succ.ctypes.data if want_success else None, count,
-                                        ctypes.byref(e._state), e._st())
+        rc = e.lib.bf_engine_read_flags(e.e, self._keep_p, self._succ_p if want_success else None, count, self._state_ref, self._stp)
         if rc:
             e._check(rc, "bf_engine_read_flags")
         e._state_fresh = True
@@ -203,48 +223,61 @@ class Session:
         from .instances import Instances3D
         c = Instances3D.__new__(Instances3D)
         object.__setattr__(c, "_image_size", image_size)
-        object.__setattr__(c, "_fields", EngineFields(self, kind, rows))
+        object.__setattr__(c, "_fields", self.fields(kind, rows))
         return c
 
-    def materialize(self, f: EngineFields):
-        """Fill an EngineFields with views of the engine state (same layout FusionEngine.export produces)."""
+    def fields(self, kind, rows) -> EngineFields:
+        if kind == "store":
+            return EngineFields(self, kind, rows, _STORE_NATIVE + tuple(self.store_chunks))
+        extras = self.cat_extras if kind == "cat" else self.map_extras
+        f = EngineFields(self, kind, rows, _MAP_NATIVE)
+        for k, v in extras.items():
+            dict.__setitem__(f, k, v)
+        return f
+
+    def view(self, f: EngineFields, k):
+        """One field of a handed-out container as a view of the engine state (same layout FusionEngine.export produces).
+        Engine-held fields are CUDA views whatever device the caller kept them on (demo.py:216-219 keeps the bookkeeping
+        fields on the host); leaving the fast path moves them back."""
         from .boxes import GeneralInstance3DBoxes
         e = self.engine
-        devs = self.store_dev if f.kind == "store" else self.map_dev
-
-        def put(k, v):
-            d = devs.get(k)
-            if d is not None and d.type == "cpu":          # the caller keeps this field on the host (demo.py:216-219): hand out a copy there
-                v = v.to(d) if isinstance(v, torch.Tensor) else v
-            dict.__setitem__(f, k, v)
         if f.kind == "store":
-            M = f.rows
-            st = e.store
-            put("scores", st["scores"][:M, 0])
-            put("pred_boxes_3d", GeneralInstance3DBoxes._wrap(st["tensor"][:M], st["R"][:M].view(M, 3, 3)))
-            put("cam_pose", st["pose"][:M].view(M, 4, 4))
-            put("projected_boxes", st["uv"][:M].view(M, 8, 2))
-            for k, chunks in self.store_chunks.items():
-                if len(chunks) > 1:
-                    merged = chunks[0]
-                    for c in chunks[1:]:
-                        merged = _cat_values(merged, c)
-                    chunks[:] = [merged]
-                put(k, chunks[0])
-            return
-        N = f.n_rows()
-        mp = e.map
-        put("scores", mp["scores"][:N])
-        put("pred_boxes", mp["box2d"][:N])
-        put("pred_proj_xy", mp["projxy"][:N])
-        put("pred_boxes_3d", GeneralInstance3DBoxes._wrap(mp["tensor"][:N], mp["R"][:N].view(N, 3, 3)))
-        put("cam_pose", mp["pose"][:N].view(N, 4, 4))
-        put("frame_id", mp["frame_id"][:N].to(torch.int64))
-        put("init_id", mp["init_id"][:N].to(torch.int64))
-        put("valid_num", mp["valid"][:N])
-        put("projected_boxes", mp["uv"][:N].view(N, 8, 2))
-        for k, v in (self.cat_extras if f.kind == "cat" else self.map_extras).items():
-            put(k, v)
+            M, st = f.rows, e.store
+            if k == "scores":
+                return st["scores"][:M, 0]
+            if k == "pred_boxes_3d":
+                return GeneralInstance3DBoxes._wrap(st["tensor"][:M], st["R"][:M].view(M, 3, 3))
+            if k == "cam_pose":
+                return st["pose"][:M].view(M, 4, 4)
+            if k == "projected_boxes":
+                return st["uv"][:M].view(M, 8, 2)
+            chunks = self.store_chunks[k]
+            if len(chunks) > 1:
+                merged = chunks[0]
+                for c in chunks[1:]:
+                    merged = _cat_values(merged, c)
+                chunks[:] = [merged]
+            return chunks[0]
+        N, mp = f.n_rows(), e.map
+        if k == "scores":
+            return mp["scores"][:N]
+        if k == "pred_boxes":
+            return mp["box2d"][:N]
+        if k == "pred_proj_xy":
+            return mp["projxy"][:N]
+        if k == "pred_boxes_3d":
+            return GeneralInstance3DBoxes._wrap(mp["tensor"][:N], mp["R"][:N].view(N, 3, 3))
+        if k == "cam_pose":
+            return mp["pose"][:N].view(N, 4, 4)
+        if k == "frame_id":
+            return mp["frame_id"][:N].to(torch.int64)
+        if k == "init_id":
+            return mp["init_id"][:N].to(torch.int64)
+        if k == "valid_num":
+            return mp["valid"][:N]
+        if k == "projected_boxes":
+            return mp["uv"][:N].view(N, 8, 2)
+        raise KeyError(k)
 
     # ---- entering: import plain containers into the engine ---------------------------------------------------------
     @staticmethod
@@ -292,7 +325,8 @@ class Session:
             e.fused["count"].fill_(F)
             if e.stream is not None:
                 e.stream.wait_stream(torch.cuda.current_stream(self.dev))
-        e._check(e.lib.bf_engine_set_counts(e.e, N, M, e._st()), "bf_engine_set_counts")
+        self._stp = e._st()
+        e._check(e.lib.bf_engine_set_counts(e.e, N, M, self._stp), "bf_engine_set_counts")
         e._state_fresh = False
         e.M, e._n_ub = M, N
         self.N, self.M = N, M
@@ -303,7 +337,7 @@ class Session:
         self.image_size = A.image_size
         # the caller's own containers become views of the engine state (in-place edits stay coherent)
         for c, kind, rows in ((A, "map", N), (P, "store", M)):
-            object.__setattr__(c, "_fields", EngineFields(self, kind, rows))
+            object.__setattr__(c, "_fields", self.fields(kind, rows))
         self.map_c, self.store_c, self.cat_c = A, P, None
         self.stage = Session.IDLE
         self.lists_host, self.lists_given = True, None
@@ -347,6 +381,7 @@ class Session:
         if bm is None or bm._session is not self:
             return
         e = self.engine
+        self._stp = e._st()
         edited = not self.lists_untouched(bm)
         if self.stage == Session.NMS:                              # the engine applies valid_num += 1 in its correspondence phase
             succ = np.nonzero(self._succ[: self.N + self.n])[0]
@@ -369,9 +404,18 @@ class Session:
         e.state()                                                  # everything issued so far has completed
         for c in (self.map_c, self.store_c, self.cat_c):
             if c is not None and isinstance(c._fields, EngineFields):
-                c._fields.fill()
-                object.__setattr__(c, "_fields", {k: (v.clone() if isinstance(v, torch.Tensor) else
-                                                      (v.clone() if hasattr(v, "clone") else v)) for k, v in dict.items(c._fields)})
+                f = c._fields
+                f.fill()
+                devs = self.store_dev if f.kind == "store" else self.map_dev
+                plain = {}
+                for k, v in dict.items(f):                         # independent copies, on the devices the caller kept the fields on
+                    d = devs.get(k)
+                    if isinstance(v, torch.Tensor):
+                        v = v.to(d) if (d is not None and d != v.device) else v.clone()
+                    elif hasattr(v, "clone"):
+                        v = v.clone()
+                    plain[k] = v
+                object.__setattr__(c, "_fields", plain)
         bm._session = None
         self.stage = Session.IDLE
         self.map_c = self.store_c = self.cat_c = self.pred = None
@@ -435,7 +479,7 @@ class Session:
         hdr[2:8] = (K3[0, 0], K3[1, 1], K3[0, 2], K3[1, 2], float(W), float(H))
         hdr[8:24] = pose.reshape(-1)
         hdr[40:56] = np.linalg.inv(pose).astype(np.float32).reshape(-1)
-        st = e._st()
+        st = self._stp = e._st()
         if e.stream is not None:
             e.stream.wait_stream(torch.cuda.current_stream(self.dev))
         rc = e.lib.bf_engine_ingest_world(e.e, hdr.ctypes.data, t.data_ptr(), R.data_ptr(), sc.data_ptr(), b2.data_ptr(),

@@ -140,7 +140,7 @@ class Instances3D:
         return ret
 
     def __len__(self) -> int:
-        if isinstance(self._fields, fastpath.EngineFields) and not self._fields.filled:
+        if isinstance(self._fields, fastpath.EngineFields):
             return self._fields.n_rows()                 # a view of the engine state: the row count is known without touching it
         for v in self._fields.values():
             return v.shape[0] if isinstance(v, (torch.Tensor, np.ndarray)) else v.__len__()
@@ -255,14 +255,21 @@ class Instances3D:
         boxes = self.get("pred_boxes_3d")
         cam_pose = self.cam_pose
         dev = ops._pick_device(boxes.tensor)
+        K = _as_numpy(K)
+        one = ops.shared_pose(cam_pose) if (boxes.tensor.is_cuda and boxes.tensor.is_contiguous() and boxes.R.is_contiguous()) else None
+        if one is not None:
+            # a keyframe's detections share one pose (demo.py:216): the reference's own inverse call (:350) on that one matrix
+            # (batched LU treats every matrix independently, so the values are identical), handed to the kernel by value
+            pose_inv = torch.linalg.inv_ex(torch.from_numpy(one)[None], check_errors=False).inverse[0].numpy()
+            self.projected_boxes = ops.project_boxes_pose(boxes.tensor, boxes.R, np.ascontiguousarray(pose_inv), K, float(W), float(H))
+            self._bf_proj = (K, H, W, one)
+            return
         corners = ops.box_corners(boxes.tensor, boxes.R)
-        # same call as the reference (:350), on cam_pose's device; a keyframe's detections share one pose, which is
-        # then inverted once (batched LU treats every matrix independently, so the values are identical)
+        # same call as the reference (:350), on cam_pose's device
         if cam_pose.shape[0] > 1 and bool((cam_pose == cam_pose[:1]).all()):
             pose_inv = torch.linalg.inv(cam_pose[:1]).expand(cam_pose.shape[0], 4, 4)
         else:
             pose_inv = torch.linalg.inv(cam_pose)
-        K = _as_numpy(K)
         uv = ops.project_boxes(corners, pose_inv.to(dev), K, float(W), float(H))
         self.projected_boxes = uv if boxes.tensor.is_cuda else uv.to(boxes.tensor.device)
         self._bf_proj = (K, H, W, cam_pose[0])              # what the engine-backed path (fastpath.py) needs to know about this keyframe

@@ -20,8 +20,9 @@ MAX_VIEWS = 64
 
 # kernels launched by one call of each entry point (the library's own __global__ functions)
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
-                    "bf_nms3d": 6, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 1, "bf_evaluate_iou": 1,
-                    "bf_detection_filter": 1, "bf_score_order": 1, "bf_points_in_hull": 1, "bf_engine_ingest_world": 1}
+                    "bf_nms3d": 5, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 1, "bf_evaluate_iou": 1,
+                    "bf_detection_filter": 1, "bf_score_order": 1, "bf_points_in_hull": 1, "bf_engine_ingest_world": 1,
+                    "bf_transform2world_pose": 1, "bf_project_boxes_pose": 1}
 
 
 class Profile:
@@ -113,6 +114,36 @@ def transform2world_(xyzlhw: torch.Tensor, R: torch.Tensor, poses) -> None:
     p = dev_tensor(poses, torch.float32, xyzlhw.device).reshape(-1, 16)
     h = handle(xyzlhw.device)
     _call(h, "bf_transform2world", h.lib.bf_transform2world, h.h, ptr(xyzlhw), ptr(R), ptr(p), xyzlhw.shape[0], h.stream())
+
+
+def shared_pose(cam_pose):
+    """The single 4x4 (contiguous float32 numpy, host) when every row of a HOST cam_pose [n,4,4] is the same matrix, else None."""
+    if isinstance(cam_pose, torch.Tensor):
+        if cam_pose.is_cuda or cam_pose.dtype != torch.float32:
+            return None
+        cam_pose = cam_pose.numpy()
+    a = np.asarray(cam_pose)
+    if a.ndim != 3 or a.shape[0] < 1 or a.dtype != np.float32 or not (a == a[0]).all():
+        return None
+    return np.ascontiguousarray(a[0])
+
+
+def transform2world_pose_(xyzlhw: torch.Tensor, R: torch.Tensor, pose16: np.ndarray) -> None:
+    """transform2world for detections that share one pose: the pose is a kernel parameter (no upload)."""
+    h = handle(xyzlhw.device)
+    Profile.h2d_bytes += 64
+    _call(h, "bf_transform2world_pose", h.lib.bf_transform2world_pose, h.h, ptr(xyzlhw), ptr(R), pose16.ctypes.data, xyzlhw.shape[0], h.stream())
+
+
+def project_boxes_pose(xyzlhw: torch.Tensor, R: torch.Tensor, pose_inv16: np.ndarray, K, W: float, H: float) -> torch.Tensor:
+    """project_3d_boxes for detections that share one pose: corners + projection in one kernel, inverse pose by value."""
+    n = xyzlhw.shape[0]
+    uv = torch.empty((n, 8, 2), dtype=torch.float32, device=xyzlhw.device)
+    h = handle(xyzlhw.device)
+    Profile.h2d_bytes += 64
+    _call(h, "bf_project_boxes_pose", h.lib.bf_project_boxes_pose, h.h, ptr(xyzlhw), ptr(R), n, pose_inv16.ctypes.data,
+          float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), float(W), float(H), ptr(uv), h.stream())
+    return uv
 
 
 def project_boxes(corners, pose_inv, K, W: float, H: float) -> torch.Tensor:

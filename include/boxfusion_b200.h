@@ -68,6 +68,15 @@ int bf_transform2world(bf_handle* h, float* xyzlhw /*[N,6]*/, float* R /*[N,9]*/
 int bf_project_boxes(bf_handle* h, const float* corners /*[N,8,3]*/, const float* pose_inv /*[N,16]*/, int N,
                      float fx, float fy, float cx, float cy, float W, float H, float* uv /*[N,8,2]*/, void* stream);
 
+/* A2 / A15 for a keyframe whose detections share ONE camera pose (demo.py:216 np.repeat-s it): the pose (A2) or its inverse
+ * (A15, torch.linalg.inv of the pose, taken by the host binding like the reference does at instances.py:350) is HOST memory,
+ * 16 floats, passed to the kernel by value - no [n,16] upload - and A15 generates the corners itself (one kernel instead of
+ * bf_box_corners + bf_project_boxes).  Bit-identical to the per-row entries above. */
+int bf_transform2world_pose(bf_handle* h, float* xyzlhw /*[N,6]*/, float* R /*[N,9]*/, const float* pose /*host [16]*/, int N, void* stream);
+int bf_project_boxes_pose(bf_handle* h, const float* xyzlhw /*[N,6] world*/, const float* R /*[N,9]*/, int N,
+                          const float* pose_inv /*host [16]*/, float fx, float fy, float cx, float cy, float W, float H,
+                          float* uv /*[N,8,2]*/, void* stream);
+
 /* ---- A3/A4  Instances3D.obb_iou / calculate_obb_iou (instances.py:106-125, 573-613) -------------
  * IoU of every (a in A) x (b in B) from corner arrays.  iou is float64 like the reference's;
  * counts (optional) receives {count1,count2,common} of the 25^3 estimator (zeros when the gate
@@ -114,7 +123,7 @@ int bf_points_in_hull(bf_handle* h, const float* corners /*[8,3]*/, const double
 /* ---- A5  the score order of nms_3d, `order = scores.argsort()[::-1]` (instances.py:52), on the device --------
  * order[r] = index of the r-th highest score; equal scores keep ascending index (a stable descending sort, what
  * torch.argsort(descending=True, stable=True) gives; NumPy's own argsort is unstable for exact ties).
- * NaN scores sort first, -0 == +0.  N <= 4096: one CTA, bitonic network in shared memory; larger N (up to 65536):
+ * NaN scores sort first, -0 == +0.  N <= 8192: one CTA, bitonic network in shared memory; larger N (up to 65536):
  * every box is ranked by counting the smaller keys (tiles through shared memory, all SMs). */
 int bf_score_order(bf_handle* h, const float* scores /*[N]*/, int N, int32_t* order /*[N]*/, void* stream);
 
@@ -216,6 +225,8 @@ typedef struct {
     int32_t check_valid;        /* box_fusion.check_valid (demo.py:297-298)                                 */
     int32_t gap;                /* data.gap in FRAMES, compared with frame ids (box_manager.py:151-166)     */
     int32_t use_graph;          /* 1: replay captured CUDA graphs; 0: issue the same launches eagerly       */
+    int32_t concurrent;         /* 1: several engines share the GPU on their own streams: the refinement uses 256-thread CTAs
+                                   (three per SM) instead of the shape that minimises the latency of a lone keyframe          */
     bf_refine_cfg refine;       /* optimiser constants; the intrinsics fields are ignored (per keyframe)    */
     const float* pst;           /* particle template [P,6], device, borrowed                                */
     int32_t P;

@@ -187,6 +187,44 @@ def load_reference():
     return ns
 
 
+class _Stub(types.ModuleType):
+    """Import-time stand-in for the viewer stack tools/utils.py pulls in (rerun, open3d); never called by what we use."""
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return _Stub(self.__name__ + "." + k)
+
+    def __call__(self, *a, **k):
+        return None
+
+
+_TOOLS = None
+
+
+def load_reference_tools():
+    """The reference's tools/utils.py (post_process :302-317, save_box :322-332, load_data :335-340), unmodified, with the
+    viewer modules it imports at the top (rerun, open3d - absent here) stubbed."""
+    global _TOOLS
+    if _TOOLS is not None:
+        return _TOOLS
+    load_reference()
+    for name in ("rerun", "rerun.blueprint", "open3d", "torchvision", "torchvision.transforms", "torchvision.transforms.functional"):
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = _Stub(name)
+    for k in [k for k in sys.modules if k == "tools" or k.startswith("tools.")]:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import tools.utils as tu
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    _TOOLS = tu
+    return tu
+
+
 def build_ref_kernel() -> str:
     """Recipe entry (called by oracle/build.py): compile the kernel string into oracle/_ref/."""
     return compile_kernel_string(extract_kernel_string())

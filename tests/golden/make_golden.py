@@ -32,6 +32,9 @@ SEQUENCES = {
     "seq_ca1m": dict(n_objects=40, seed=1, max_det=20, shape="ca1m", tilt_noise=0.0, frames=12),
     "seq_scannet_tilt": dict(n_objects=40, seed=2, max_det=20, shape="scannet", tilt_noise=0.02, frames=10),
 }
+# a keyframe every 3rd frame (cfg data.gap = 3 like config/ca1m.yaml's 20 / scannet.yaml's 25 in spirit) with
+# BoxManager.check_valid_num switched on: frame ids and the `count - gap` threshold are in FRAMES (demo.py:217, 297-298)
+GAP_SEQUENCE = ("seq_gap3_valid", dict(n_objects=40, seed=21, max_det=12, shape="scannet", new_frac=0.35, frames=10), 3)
 
 
 def gen_pst(ref):
@@ -42,12 +45,15 @@ def gen_pst(ref):
     return pst
 
 
-def gen_sequence(ref, name, spec):
+def gen_sequence(ref, name, spec, gap=1):
     spec = dict(spec)
     frames = spec.pop("frames")
     scene = SyntheticScene(**spec)
     cfg = make_cfg(spec["shape"], pst_path=REF_PST, pst_size=1024)
-    sess = FusionSession(ref, cfg)
+    if gap > 1:
+        cfg["data"]["gap"] = gap
+        cfg["box_fusion"]["check_valid"] = True
+    sess = FusionSession(ref, cfg, frame_stride=gap)
     out = {"n_frames": np.array(frames)}
     for k in range(frames):
         kf = scene.keyframe(k)
@@ -160,10 +166,99 @@ def gen_hull_helpers(ref):
     print("hull_helpers: gate true for", int(gate.sum()), "of", len(gate), "pairs; inside", int(np.stack(inside).sum()), "of", np.stack(inside).size)
 
 
+def gen_prefilters(ref):
+    """The detection pre-filters (box_manager.py:217-245; demo.py:140-148) and the pose-disparity methods
+    (box_manager.py:168-215) of the unmodified reference on seeded inputs: `python tests/golden/make_golden.py extras`."""
+    rs = np.random.RandomState(0)
+    n = 4000
+    dims = np.exp(rs.normal(np.log(0.4), 1.0, (n, 3))).astype(np.float32)
+    dims[:200, 0] = 3.0; dims[:200, 1] = 0.05                                  # floor-like slabs
+    dims[200:300] = np.array([0.14, 0.13, 1.2], np.float32) * rs.uniform(0.9, 1.1, (100, 3)).astype(np.float32)
+    dims[300:340] = np.array([1.5, 0.1, 0.1], np.float32)                      # exactly on the ratio thresholds (15, 7.5, 20, 10)
+    dims[340:380] = np.array([2.0, 0.1, 0.1], np.float32)
+    t = np.concatenate([rs.normal(0, 2, (n, 3)).astype(np.float32), dims], 1)
+    uv = np.stack([rs.uniform(-20, 404, n), rs.uniform(-20, 532, n)], 1).astype(np.float32)
+    uv[:50, 0] = np.array([38.0, 39.0, 345.0, 346.0, 64.0] * 10, np.float32)   # on / next to the integer bounds of both shapes
+    uv[:50, 1] = np.array([51.0, 52.0, 460.0, 461.0, 48.0] * 10, np.float32)
+    out = {"tensor": t, "uv": uv}
+    tt, uu = torch.from_numpy(t), torch.from_numpy(uv)
+    for shape in ("ca1m", "scannet"):
+        cfg = make_cfg(shape)
+        bm = ref.BoxManager(cfg)
+        W, H = cfg["cam"]["W"], cfg["cam"]["H"]
+        for ratio in (cfg["detection"]["uv_bound_value"], 1.0, 0.75):
+            out[f"{shape}_uv_{ratio}"] = bm.check_uv_bounds(uu, W, H, ratio=ratio).numpy()
+        for ratio in (cfg["detection"]["floor_ratio"], 20):
+            out[f"{shape}_floor_{ratio}"] = bm.check_floor_mask(tt, ratio=ratio).numpy()
+        for thres in (0.5, 2.5):
+            out[f"{shape}_large_{thres}"] = bm.check_large_mask(tt, thres=thres).numpy()
+    # pose disparity: random rigid poses incl. identical pairs, pure translations, 180-degree turns
+    m = 600
+    poses = np.tile(np.eye(4, dtype=np.float32), (m, 1, 1))
+    for i in range(m):
+        a = rs.normal(0, 1, (3, 3)); q, _ = np.linalg.qr(a)
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        poses[i, :3, :3] = q.astype(np.float32)
+        poses[i, :3, 3] = rs.normal(0, 1.5, 3).astype(np.float32)
+    poses[1] = poses[0]                                                         # identical
+    poses[3, :3, :3] = poses[2, :3, :3]                                          # pure translation
+    poses[5, :3, :3] = poses[4, :3, :3] @ np.diag([-1.0, -1.0, 1.0]).astype(np.float32)   # 180 degrees
+    ia, ib = rs.randint(0, m, 1500), rs.randint(0, m, 1500)
+    ia[:3], ib[:3] = [0, 2, 4], [1, 3, 5]
+    centers = rs.normal(0, 1, (m, 3))
+    bm = ref.BoxManager(make_cfg("ca1m"))
+    P = torch.from_numpy(poses)
+    res = np.zeros((1500, 4), np.float64)
+    for k, (a, b) in enumerate(zip(ia, ib)):
+        base, ang, score, cd = bm.compute_pose_center_disparity(P[a], P[b], centers[a], centers[b])
+        b2, a2, s2 = bm.compute_pose_disparity(P[a], P[b])
+        assert float(b2) == float(base) and (float(a2) == float(ang) or (np.isnan(float(a2)) and np.isnan(float(ang))))
+        res[k] = (float(base), float(ang), float(score), float(cd))
+    out.update(poses=poses, ia=ia, ib=ib, centers=centers, disparity=res)
+    np.savez_compressed(os.path.join(HERE, "prefilters.npz"), **out)
+    print("prefilters:", {k: int(v.sum()) for k, v in out.items() if v.dtype == np.bool_})
+
+
+def gen_results(ref):
+    """Result / wire formats: the reference's own tools/utils.py post_process / save_box (:302-332) on corner arrays, and the
+    two save lists demo.py:369-387 builds from them (those five lines are transcribed here: demo.py itself cannot run)."""
+    import pickle
+    import tempfile
+    tu = rh.load_reference_tools()
+    rs = np.random.RandomState(3)
+    (mt, mR, _), _ = map_and_detections(60, 8, seed=4, tilt_noise=0.01)
+    mt[:20, 3:] *= rs.uniform(0.1, 0.6, (20, 3)).astype(np.float32)              # some boxes below the 0.3 m ScanNet size filter
+    corners = ref.GeneralInstance3DBoxes(torch.from_numpy(mt), torch.from_numpy(mR)).corners.cpu().numpy()
+    kept = tu.post_process(corners)                                               # tools/utils.py:302-317 (default threshold 0.3)
+    kept05 = tu.post_process(corners, threshold=0.5)
+    save_list = [[(int(0), (kept[n]), 1.0) for n in range(len(kept))]]            # demo.py:376-378 after post_process (scannet)
+    feats = rs.normal(0, 1, (len(corners), 16)).astype(np.float32)
+    cls = rs.randint(0, 30, len(corners))
+    all_save_list = [[(cls[n], (corners[n]), feats[n]) for n in range(len(corners))]]     # demo.py:383-386
+    d = tempfile.mkdtemp()
+    with contextlib.redirect_stdout(io.StringIO()):
+        tu.save_box(save_list, os.path.join(d, "a.pkl"))
+        tu.save_box(all_save_list, os.path.join(d, "b.pkl"))
+    back = tu.load_data(os.path.join(d, "a.pkl"))
+    assert len(back[0]) == len(kept)
+    np.savez_compressed(os.path.join(HERE, "results_formats.npz"), tensor=mt, R=mR, corners=corners, kept=kept, kept05=kept05,
+                        features=feats, classes=cls,
+                        global_pkl=np.frombuffer(open(os.path.join(d, "a.pkl"), "rb").read(), dtype=np.uint8),
+                        framewise_pkl=np.frombuffer(open(os.path.join(d, "b.pkl"), "rb").read(), dtype=np.uint8),
+                        pickle_protocol=np.array(pickle.HIGHEST_PROTOCOL))
+    print("results_formats: post_process keeps", len(kept), "of", len(corners), "(0.5:", len(kept05), ")")
+
+
 def main():
     ref = rh.load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "helpers":
         gen_hull_helpers(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "extras":       # round 2 fixtures, without touching the round-1 ones
+        gen_prefilters(ref)
+        gen_results(ref)
+        gen_sequence(ref, GAP_SEQUENCE[0], GAP_SEQUENCE[1], gap=GAP_SEQUENCE[2])
         return
     pst = gen_pst(ref)
     for name, spec in SEQUENCES.items():
@@ -171,6 +266,9 @@ def main():
     gen_iou_pairs(ref)
     gen_refine(ref, pst)
     gen_hull_helpers(ref)
+    gen_prefilters(ref)
+    gen_results(ref)
+    gen_sequence(ref, GAP_SEQUENCE[0], GAP_SEQUENCE[1], gap=GAP_SEQUENCE[2])
     import scipy
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "torch": torch.__version__,
             "reference": "pliam1105/BoxFusion @ /root/reference", "sequences": SEQUENCES,

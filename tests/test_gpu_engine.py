@@ -101,6 +101,31 @@ def test_check_valid_num_three_way():
     assert dropped > 0, "the scene must exercise check_valid_num"
 
 
+def test_frame_gap_sequence_matches_reference_golden(golden_dir):
+    """A keyframe every 3rd frame with check_valid_num on (data.gap is in frames): the engine, given the
+    frame index of every keyframe, and the reference-shaped API both equal the reference golden after every keyframe."""
+    from tests.golden.make_golden import GAP_SEQUENCE
+    name, spec, gap = GAP_SEQUENCE
+    spec = dict(spec)
+    n_frames = spec.pop("frames")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = make_cfg(spec["shape"], pst_path=os.path.join(golden_dir, "pst_1024_0.npy"), pst_size=1024)
+    cfg["data"]["gap"] = gap
+    cfg["box_fusion"]["check_valid"] = True
+    scene = SyntheticScene(**spec)
+    eng = FusionEngine(cfg, map_capacity=512, store_capacity=4096, fused_capacity=1024)
+    sess = FusionSession(api, cfg, device="cuda", frame_stride=gap)
+    for k in range(n_frames):
+        kf = scene.keyframe(k)
+        eng.step(_pack(kf), kf.tensor_cam.shape[0], kf.K, kf.image_size, frame_id=gap * k)
+        sess.step(kf)
+        a, b = eng.snapshot(), sess.snapshot()
+        for key in KEYS:
+            ref = g[f"k{k}_snap_{key}"]
+            assert a[key].shape == ref.shape and np.array_equal(_bits(a[key]), _bits(ref)), ("engine", k, key)
+            assert b[key].shape == ref.shape and np.array_equal(_bits(b[key]), _bits(ref)), ("api", k, key)
+
+
 def test_engine_graph_equals_eager_and_phase_by_phase():
     """The captured whole-keyframe graph, the same launches issued eagerly, and the keyframe issued phase by phase (what the
     reference-shaped API does) leave identical state."""

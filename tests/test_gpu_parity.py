@@ -59,6 +59,26 @@ def test_lift_and_project_match_reference_golden(golden_dir):
 
 # ---- A3/A4 oriented-3D IoU --------------------------------------------------------------------------
 
+def test_shared_pose_entries_equal_per_row_entries():
+    """bf_transform2world_pose / bf_project_boxes_pose (one pose per keyframe, passed by value; corners + projection fused)
+    are bit-identical to bf_transform2world / bf_box_corners + bf_project_boxes."""
+    scene = SyntheticScene(n_objects=60, seed=4, max_det=40, tilt_noise=0.02)
+    for k in (0, 3, 7):
+        kf = scene.keyframe(k)
+        n = kf.tensor_cam.shape[0]
+        poses = torch.from_numpy(np.repeat(kf.pose[None], n, axis=0))
+        t1, r1 = torch.from_numpy(kf.tensor_cam).cuda(), torch.from_numpy(kf.R_cam).cuda().contiguous()
+        t2, r2 = t1.clone(), r1.clone()
+        ops.transform2world_(t1, r1, poses)
+        ops.transform2world_pose_(t2, r2, ops.shared_pose(poses))
+        assert torch.equal(t1, t2) and torch.equal(r1, r2)
+        inv = torch.linalg.inv(poses)
+        uv1 = ops.project_boxes(ops.box_corners(t1, r1), inv, kf.K, float(kf.image_size[0]), float(kf.image_size[1]))
+        uv2 = ops.project_boxes_pose(t2, r2, np.ascontiguousarray(inv[0].numpy()), kf.K, float(kf.image_size[0]), float(kf.image_size[1]))
+        assert torch.equal(uv1, uv2)
+    assert ops.shared_pose(torch.stack([poses[0], poses[0] + 1])) is None
+
+
 def test_sampled_iou_matches_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "iou_pairs.npz"))
     iou = ops.iou3d_matrix(g["corners"], g["corners"]).cpu().numpy()
@@ -282,7 +302,7 @@ def test_score_order_matches_stable_descending_argsort():
     """bf_score_order == torch.argsort(descending=True, stable=True) (the order nms_3d consumes, instances.py:52), incl. exact
     ties (ascending index), -0/+0, NaN first, every size class of the bitonic network."""
     rs = np.random.RandomState(4)
-    for n in (1, 2, 3, 31, 32, 33, 250, 1000, 1024, 1025, 4095, 4096):
+    for n in (1, 2, 3, 31, 32, 33, 250, 1000, 1024, 1025, 4095, 4096, 4352, 8191, 8192):
         s = rs.uniform(0.0, 1.0, n).astype(np.float32)
         if n > 8:
             s[rs.randint(0, n, n // 4)] = s[rs.randint(0, n, n // 4)]          # exact ties
@@ -293,7 +313,7 @@ def test_score_order_matches_stable_descending_argsort():
         want = torch.argsort(t, descending=True, stable=True).to(torch.int32)
         got = ops.score_order(t)
         assert torch.equal(want, got), n
-    for n in (4097, 4352, 5000, 20000, 65536):                                  # beyond the single-CTA limit: rank by counting, all SMs
+    for n in (8193, 9000, 20000, 65536):                                  # beyond the single-CTA limit: rank by counting, all SMs
         s = rs.uniform(0.0, 1.0, n).astype(np.float32)
         s[rs.randint(0, n, n // 4)] = s[rs.randint(0, n, n // 4)]
         s[1], s[5], s[3], s[7] = 0.0, -0.0, np.nan, -1.5
@@ -390,7 +410,7 @@ def test_refine_persistent_clusters_match_one_cluster_per_box():
         for G in (1, 3, 7, 64):
             h.check(h.lib.bf_set_option(h.h, _lib.OPT_REFINE_PERSISTENT, G), "bf_set_option")
             got = ops.refine(*args, want_trace=True, max_views=V)
-            assert ops.last_refine_launch() == {"variant": "latency", "cluster": 16, "threads": 512}
+            assert ops.last_refine_launch() == {"variant": "latency", "cluster": 8, "threads": 512}    # 64 particles per CTA
             for a, b in zip(ref[:4], got[:4]):
                 assert torch.equal(a, b), G
             assert int(got[4].item()) == 0

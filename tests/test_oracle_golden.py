@@ -116,6 +116,70 @@ def test_lift_and_project_match_golden(golden_dir):
         assert np.array_equal(_bits(ins.projected_boxes.numpy()), _bits(g[f"k{k}_projected"]))
 
 
+# ---- round 2 pins: detection pre-filters, pose disparity, result formats, frame-unit gap -----------------------------
+
+def test_port_prefilters_match_reference_golden(golden_dir):
+    """oracle/port.py's check_uv_bounds / check_floor_mask / check_large_mask == the reference's (box_manager.py:217-245)."""
+    g = np.load(os.path.join(golden_dir, "prefilters.npz"))
+    tt, uu = torch.from_numpy(g["tensor"]), torch.from_numpy(g["uv"])
+    for shape in ("ca1m", "scannet"):
+        cfg = make_cfg(shape)
+        bm = port.BoxManager(cfg)
+        W, H = cfg["cam"]["W"], cfg["cam"]["H"]
+        for ratio in (cfg["detection"]["uv_bound_value"], 1.0, 0.75):
+            assert np.array_equal(bm.check_uv_bounds(uu, W, H, ratio=ratio).numpy(), g[f"{shape}_uv_{ratio}"])
+        for ratio in (cfg["detection"]["floor_ratio"], 20):
+            assert np.array_equal(bm.check_floor_mask(tt, ratio=ratio).numpy(), g[f"{shape}_floor_{ratio}"])
+        for thres in (0.5, 2.5):
+            assert np.array_equal(bm.check_large_mask(tt, thres=thres).numpy(), g[f"{shape}_large_{thres}"])
+
+
+def test_port_pose_disparity_matches_reference_golden(golden_dir):
+    """compute_pose_disparity / compute_pose_center_disparity (box_manager.py:168-215): bit-identical (same torch ops)."""
+    g = np.load(os.path.join(golden_dir, "prefilters.npz"))
+    bm = port.BoxManager(make_cfg("ca1m"))
+    P = torch.from_numpy(g["poses"])
+    for k in range(0, len(g["ia"]), 7):
+        a, b = int(g["ia"][k]), int(g["ib"][k])
+        base, ang, score, cd = bm.compute_pose_center_disparity(P[a], P[b], g["centers"][a], g["centers"][b])
+        got = np.array([float(base), float(ang), float(score), float(cd)])
+        assert np.array_equal(got, g["disparity"][k], equal_nan=True), k
+
+
+def test_port_sequence_with_frame_gap_matches_reference_golden(golden_dir):
+    """A keyframe every 3rd frame, check_valid_num on: frame ids and the `count - gap` threshold are in FRAMES."""
+    from tests.golden.make_golden import GAP_SEQUENCE
+    name, spec, gap = GAP_SEQUENCE
+    spec = dict(spec)
+    n_frames = spec.pop("frames")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    port.IOU_BACKEND = "c"
+    cfg = make_cfg(spec["shape"], pst_path=os.path.join(golden_dir, "pst_1024_0.npy"), pst_size=1024)
+    cfg["data"]["gap"] = gap
+    cfg["box_fusion"]["check_valid"] = True
+    scene = SyntheticScene(**spec)
+    sess = FusionSession(port, cfg, frame_stride=gap)
+    dropped = 0
+    for k in range(n_frames):
+        sess.step(scene.keyframe(k))
+        snap = sess.snapshot()
+        for key, val in snap.items():
+            ref = g[f"k{k}_snap_{key}"]
+            assert val.shape == ref.shape and np.array_equal(_bits(val), _bits(ref)), (k, key)
+        if sess.last_keep_idx is not None:
+            dropped += max(0, len(sess.last_keep_idx) - len(sess.all_pred_box))
+    assert dropped > 0, "the golden sequence must exercise check_valid_num"
+
+
+def test_result_formats_host_part_matches_reference_golden(golden_dir):
+    """results.post_process == the reference's tools/utils.py post_process (:302-317) on the golden corner arrays."""
+    from boxfusion_b200 import results
+    g = np.load(os.path.join(golden_dir, "results_formats.npz"))
+    assert np.array_equal(results.post_process(g["corners"]), g["kept"])
+    assert np.array_equal(results.post_process(g["corners"], threshold=0.5), g["kept05"])
+    assert np.array_equal(results.post_process(torch.from_numpy(g["corners"])).numpy(), g["kept"])
+
+
 # ---- live pinning (build container only) ------------------------------------------------------
 
 needs_ref = pytest.mark.skipif(not rh.reference_available(), reason="/root/reference not present")
