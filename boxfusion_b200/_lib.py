@@ -91,6 +91,8 @@ PROTOTYPES = {
     "bf_iou3d_matrix": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bf_nms3d": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _f32, _f32, _f32, _i32,
                         _vp, _vp, _vp, _vp]),
+    "bf_nms3d_edges": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _f64, _i32, _vp, _i32, _vp, _vp]),
+    "bf_nms3d_greedy": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "bf_corr2d": (_i32, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "bf_points_in_hull": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bf_score_order": (_i32, [_vp, _vp, _i32, _vp, _vp]),

@@ -125,20 +125,21 @@ __device__ __forceinline__ void bf_record_head(const bf_record_ctx& ctx, const u
 __global__ void __launch_bounds__(1024)
 bf_greedy_kernel(const unsigned long long* __restrict__ edges, const unsigned long long* __restrict__ counters,
                  const bf_dimref Nd, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ rowany,
-                 unsigned long long* __restrict__ live, bf_record_ctx ctx, int32_t* __restrict__ success) {
+                 unsigned long long* __restrict__ live, bf_record_ctx ctx, int32_t* __restrict__ success, int n_slots) {
     extern __shared__ unsigned long long s_keys[];
     __shared__ int s_E;
     const int N = bf_dim(Nd);
     const int W = (N + 31) >> 5;
-    const unsigned long long E64 = counters[6];
+    // n_slots >= 0: `edges` is a gathered list of that many slots, empty ones hold ~0 (they sort last); else the IoU stage's counters
+    const unsigned long long E64 = n_slots >= 0 ? (unsigned long long)n_slots : counters[6];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
-    if (tid == 0 && counters[5]) atomicExch(ctx.status, BF_ERR_CAPACITY);       // the IoU stage's candidate list overflowed (fixed-size scratch)
+    if (tid == 0 && n_slots < 0 && counters[5]) atomicExch(ctx.status, BF_ERR_CAPACITY);   // the IoU stage's candidate list overflowed (fixed-size scratch)
     const bool dense = E64 > BF_EDGE_CAP;
     if (dense && !mask) {
         if (tid == 0) atomicExch(ctx.status, BF_ERR_CAPACITY);                   // no dense mask for maps this large
         return;
     }
-    const int E_sparse = dense ? 0 : (int)E64;
+    int E_sparse = dense ? 0 : (int)E64;
     int n2 = 1;
     while (n2 < E_sparse) n2 <<= 1;
     // shared memory: [sorted keys (sparse path only)] [remaining bit set] [live flags (sparse path only)]
@@ -153,8 +154,17 @@ bf_greedy_kernel(const unsigned long long* __restrict__ edges, const unsigned lo
     const unsigned char* actp;
     int E;
     if (!dense) {
-        for (int i = tid; i < n2; i += T) s_keys[i] = (i < E_sparse) ? edges[i] : ~0ULL;
+        if (tid == 0) s_E = 0;
         __syncthreads();
+        int valid = 0;
+        for (int i = tid; i < n2; i += T) {
+            const unsigned long long key = (i < E_sparse) ? edges[i] : ~0ULL;
+            s_keys[i] = key;
+            valid += (key != ~0ULL) ? 1 : 0;
+        }
+        if (valid) atomicAdd(&s_E, valid);
+        __syncthreads();
+        E_sparse = s_E;                                        // real edges (gathered lists carry empty slots)
         for (int k = 2; k <= n2; k <<= 1)                      // bitonic sort, ascending
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int i = tid; i < n2; i += T) {
@@ -267,7 +277,7 @@ int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_di
             bf_rank_kernel<<<bf_blocks(N, 128) < 64 ? bf_blocks(N, 128) : 64, 128, 0, st>>>(order, Nd, rank);
             BF_LAUNCH_CHECK(h, "bf_rank_kernel");
         }
-        if ((rc = bf_iou3d_run(h, corners, Nd, corners, Nd, 1, mode, nullptr, nullptr, nullptr, iou_threshold, rank, mask,
+        if ((rc = bf_iou3d_run(h, corners, Nd, corners, Nd, 1, 0, mode, nullptr, nullptr, nullptr, iou_threshold, rank, mask,
                                rowany, edges, BF_EDGE_CAP, st)))
             return rc;
         if (Nd.dev || (long long)N * N <= (long long)(h->cap[BF_SCRATCH_WORK] / 8)) break;   // cannot overflow / checked by the engine's status word
@@ -285,7 +295,68 @@ int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_di
     // sorted edge list in shared memory (keys + remaining bit set + live flags); the dense path needs the bit set only
     const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
     BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-    bf_greedy_kernel<<<1, 1024, smem_e, st>>>(edges, counters, Nd, dense ? mask : nullptr, rowany, live, ctx, success);
+    bf_greedy_kernel<<<1, 1024, smem_e, st>>>(edges, counters, Nd, dense ? mask : nullptr, rowany, live, ctx, success, -1);
+    BF_LAUNCH_CHECK(h, "bf_greedy_kernel");
+    return BF_OK;
+}
+
+// ---- the two halves of bf_nms3d as separate entries (SURVEY.md section 8(e) axis 3): the over-threshold pairs of a block
+// of rows of the pair triangle, and the greedy scan + record() over a (gathered) edge list -------------------------------
+__global__ void bf_edges_finish_kernel(unsigned long long* __restrict__ edges, int cap, const unsigned long long* __restrict__ counters,
+                                       int32_t* __restrict__ status) {
+    const unsigned long long E = counters[6];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (E > (unsigned long long)cap || counters[5])) atomicExch(status, BF_ERR_CAPACITY);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
+        if ((unsigned long long)i >= E) edges[i] = ~0ULL;          // empty slots sort last
+}
+
+extern "C" int bf_nms3d_edges(bf_handle* h, const float* corners, int N, const int32_t* order, int row_begin, int row_end,
+                              double iou_threshold, int mode, unsigned long long* edges, int edge_cap, int32_t* status, void* stream) {
+    bf_device_guard guard(h);
+    if (!h || N < 0 || N > 65536 || row_begin < 0 || row_end < row_begin || row_end > N || edge_cap < 1 || edge_cap > BF_EDGE_CAP)
+        return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d_edges", "bad size");
+    if (!corners || !order || !edges || !status) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d_edges", "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    void* p;
+    int rc;
+    if ((rc = bf_scratch(h, BF_SCRATCH_RANK, sizeof(int32_t) * (size_t)(N > 0 ? N : 1), &p))) return rc;
+    int32_t* rank = (int32_t*)p;
+    if ((rc = bf_scratch(h, BF_SCRATCH_COUNTERS, sizeof(unsigned long long) * 8, &p))) return rc;
+    const int M = row_end - row_begin;
+    if (N > 0) {
+        bf_rank_kernel<<<bf_blocks(N, 128) < 64 ? bf_blocks(N, 128) : 64, 128, 0, st>>>(order, bf_dim_host(N), rank);
+        BF_LAUNCH_CHECK(h, "bf_rank_kernel");
+    }
+    if (M > 0) {
+        if ((rc = bf_scratch(h, BF_SCRATCH_WORK, 8 * ((size_t)M * N < (1u << 20) ? (size_t)M * N : (size_t)(1u << 20) + 64 * (size_t)(M + N)), &p))) return rc;
+        if ((rc = bf_iou3d_run(h, corners + 24 * (size_t)row_begin, bf_dim_host(M), corners, bf_dim_host(N), 1, row_begin, mode, nullptr, nullptr,
+                               nullptr, iou_threshold, rank, nullptr, nullptr, edges, edge_cap, st)))
+            return rc;
+    } else {
+        BF_CUDA(h, cudaMemsetAsync(h->buf[BF_SCRATCH_COUNTERS], 0, sizeof(unsigned long long) * 8, st));
+    }
+    bf_edges_finish_kernel<<<8, 256, 0, st>>>(edges, edge_cap, (const unsigned long long*)h->buf[BF_SCRATCH_COUNTERS], status);
+    BF_LAUNCH_CHECK(h, "bf_edges_finish_kernel");
+    return BF_OK;
+}
+
+extern "C" int bf_nms3d_greedy(bf_handle* h, const unsigned long long* edges, int n_slots, const float* centers, int N, const int32_t* order,
+                               const int32_t* init_id, const float* poses, int32_t* fusion_list, int32_t* fusion_len, int32_t* fusion_flag,
+                               float translation_gap, float rotation_gap_deg, float center_gap, int32_t* keep, int32_t* success,
+                               int32_t* status, void* stream) {
+    bf_device_guard guard(h);
+    if (!h || N < 0 || N > 65536 || n_slots < 0 || n_slots > BF_EDGE_CAP) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d_greedy", "bad size");
+    if (N == 0) return BF_OK;
+    if (!edges || !centers || !order || !init_id || !poses || !fusion_list || !fusion_len || !fusion_flag || !keep || !success || !status)
+        return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d_greedy", "null pointer");
+    bf_record_ctx ctx;
+    ctx.order = order; ctx.init_id = init_id; ctx.poses = poses; ctx.centers = centers; ctx.fl = fusion_list;
+    ctx.flen = fusion_len; ctx.fflag = fusion_flag; ctx.keep = keep; ctx.status = status;
+    ctx.translation_gap = translation_gap; ctx.rotation_gap = rotation_gap_deg; ctx.center_gap = center_gap;
+    const int W = (N + 31) / 32;
+    const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
+    BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    bf_greedy_kernel<<<1, 1024, smem_e, (cudaStream_t)stream>>>(edges, nullptr, bf_dim_host(N), nullptr, nullptr, nullptr, ctx, success, n_slots);
     BF_LAUNCH_CHECK(h, "bf_greedy_kernel");
     return BF_OK;
 }

@@ -12,7 +12,7 @@ struct bf_record_ctx {
 };
 
 // K1 (bf_iou3d.cu)
-int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float* cornersB, bf_dimref Nd, int triangle, int mode,
+int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float* cornersB, bf_dimref Nd, int triangle, int a_off, int mode,
                  double* iou, int32_t* counts, int64_t* stats, double thr, const int32_t* rank, uint32_t* mask,
                  uint32_t* rowany, unsigned long long* edges, int edge_cap, cudaStream_t st);
 int bf_iou3d_overflowed(bf_handle* h, cudaStream_t st, int* overflow);

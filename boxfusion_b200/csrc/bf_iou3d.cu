@@ -132,7 +132,7 @@ __device__ inline bool bf_analytic_iou(const float* __restrict__ ca, const float
 __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA,
                                 const double* __restrict__ planesA, const bf_dimref Md, const float* __restrict__ cornersB,
                                 const float* __restrict__ aabbB, const double* __restrict__ planesB, const bf_dimref Nd,
-                                int triangle, int mode, double* __restrict__ iou, int32_t* __restrict__ counts,
+                                int triangle, int a_off, int mode, double* __restrict__ iou, int32_t* __restrict__ counts,
                                 bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
                                 // NMS outputs (ANALYTIC hits are thresholded here)
                                 double thr, const int32_t* __restrict__ rank, uint32_t* __restrict__ mask,
@@ -141,12 +141,13 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
     const int W = (N + 31) >> 5;
     const long long total = (long long)M * N;
     const long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p0 == 0) counters[1] = triangle ? (unsigned long long)M * (unsigned long long)(M > 0 ? M - 1 : 0) / 2ULL : (unsigned long long)total;
+    // triangle: A is rows [a_off, a_off + M) of B and only pairs with a_off + a < b are evaluated
+    if (p0 == 0) counters[1] = triangle ? (unsigned long long)M * (unsigned long long)(2LL * (N - a_off) - M - 1 > 0 ? 2LL * (N - a_off) - M - 1 : 0) / 2ULL : (unsigned long long)total;
     for (long long p = p0; p < total; p += (long long)gridDim.x * blockDim.x) {
         const int a = (int)(p / N), b = (int)(p % N);
         if (iou) iou[p] = 0.0;
         if (counts) { counts[3 * p] = 0; counts[3 * p + 1] = 0; counts[3 * p + 2] = 0; }
-        if (triangle && a >= b) continue;
+        if (triangle && a + a_off >= b) continue;
         // exact reject: a point within 1e-6 of every face plane of a box lies within its AABB grown by 1e-4
         const float* ba = aabbA + 6 * a;
         const float* bb = aabbB + 6 * b;
@@ -163,7 +164,7 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
                 atomicAdd(&counters[4], 1ULL);
                 if (iou) iou[p] = v;
                 if (rank && v > thr) {
-                    const int ra = rank[a], rb = rank[b];
+                    const int ra = rank[a + a_off], rb = rank[b];
                     const int r0 = min(ra, rb), r1 = max(ra, rb);
                     if (mask) {
                         atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
@@ -187,7 +188,7 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
 __global__ void __launch_bounds__(BF_COUNT_THREADS)
 bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA, const double* __restrict__ planesA,
                 const float* __restrict__ cornersB, const float* __restrict__ aabbB, const double* __restrict__ planesB,
-                const bf_dimref Nd, const bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
+                const bf_dimref Nd, int a_off, const bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
                 double* __restrict__ iou, int32_t* __restrict__ counts, double thr, const int32_t* __restrict__ rank,
                 uint32_t* __restrict__ mask, uint32_t* __restrict__ rowany, unsigned long long* __restrict__ edges,
                 int edge_cap) {
@@ -254,7 +255,7 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
             if (iou) iou[p] = v;
             if (counts) { counts[3 * p] = n1; counts[3 * p + 1] = n2; counts[3 * p + 2] = n12; }
             if (rank && v > thr) {
-                const int ra = rank[a], rb = rank[b];
+                const int ra = rank[a + a_off], rb = rank[b];
                 const int r0 = min(ra, rb), r1 = max(ra, rb);
                 if (mask) {
                     atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
@@ -271,7 +272,7 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
 // Host driver shared by bf_iou3d_matrix, bf_nms3d and the engine step.  Md / Nd: sizes on the host, or upper bounds on
 // the host + the actual sizes in device memory (the captured engine step: scratch is sized for the bounds, the grids are
 // fixed and the kernels stride).  The counters are zeroed here.
-int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float* cornersB, bf_dimref Nd, int triangle, int mode,
+int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float* cornersB, bf_dimref Nd, int triangle, int a_off, int mode,
                  double* iou, int32_t* counts, int64_t* stats, double thr, const int32_t* rank, uint32_t* mask,
                  uint32_t* rowany, unsigned long long* edges, int edge_cap, cudaStream_t st) {
     double *plA = nullptr, *plB = nullptr;
@@ -312,12 +313,12 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float*
         const long long gcap = (long long)h->sm_count * (dev_sized ? 16 : 64);
         if (g > gcap) g = gcap;
         if (g < 1) g = 1;
-        bf_pairs_kernel<<<(unsigned)g, 128, 0, st>>>(cornersA, bbA, plA, Md, cornersB, bbB, plB, Nd, triangle, mode,
+        bf_pairs_kernel<<<(unsigned)g, 128, 0, st>>>(cornersA, bbA, plA, Md, cornersB, bbB, plB, Nd, triangle, a_off, mode,
                                                      iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, edges, edge_cap);
     }
     BF_LAUNCH_CHECK(h, "bf_pairs_kernel");
     const int grid = h->sm_count * 3;
-    bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, Nd, work, (int)cap, counters,
+    bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, Nd, a_off, work, (int)cap, counters,
                                                        iou, counts, thr, rank, mask, rowany, edges, edge_cap);
     BF_LAUNCH_CHECK(h, "bf_count_kernel");
     if (stats)   // pairs, AABB-passing, gate-passing, analytic
@@ -344,7 +345,7 @@ extern "C" int bf_iou3d_matrix(bf_handle* h, const float* cornersA, int M, const
     if (!cornersA || !cornersB || !iou) return bf_fail(h, BF_ERR_INVALID_ARG, "bf_iou3d_matrix", "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        int rc = bf_iou3d_run(h, cornersA, bf_dim_host(M), cornersB, bf_dim_host(N), 0, mode, iou, counts, stats, 0.0, nullptr,
+        int rc = bf_iou3d_run(h, cornersA, bf_dim_host(M), cornersB, bf_dim_host(N), 0, 0, mode, iou, counts, stats, 0.0, nullptr,
                               nullptr, nullptr, nullptr, 0, st);
         if (rc) return rc;
         if ((long long)M * N <= (long long)(h->cap[BF_SCRATCH_WORK] / sizeof(bf_work_item))) break;   // cannot overflow

@@ -22,7 +22,8 @@ MAX_VIEWS = 64
 KERNELS_PER_CALL = {"bf_box_corners": 1, "bf_transform2world": 1, "bf_project_boxes": 1, "bf_iou3d_matrix": 4,
                     "bf_nms3d": 5, "bf_corr2d": 2, "bf_pose_disparity": 1, "bf_refine": 1, "bf_evaluate_iou": 1,
                     "bf_detection_filter": 1, "bf_score_order": 1, "bf_points_in_hull": 1, "bf_engine_ingest_world": 1,
-                    "bf_transform2world_pose": 1, "bf_project_boxes_pose": 1}
+                    "bf_transform2world_pose": 1, "bf_project_boxes_pose": 1,
+                    "bf_nms3d_edges": 5, "bf_nms3d_greedy": 1}
 
 
 class Profile:
@@ -193,6 +194,37 @@ def nms3d(corners, centers, order, init_id, poses, fusion_list, fusion_len, fusi
                            ptr(fusion_list), ptr(fusion_len), ptr(fusion_flag), float(iou_threshold),
                            float(translation_gap), float(rotation_gap), float(center_gap), int(mode),
                            ptr(keep), ptr(success), ptr(status), h.stream())
+    return keep, success, status
+
+
+EDGE_CAP = 8192
+
+
+def nms3d_edges(corners, order, row_begin: int, row_end: int, iou_threshold: float, mode: int = IOU_SAMPLED_REF, edge_cap: int = EDGE_CAP):
+    """Over-threshold pairs of rows [row_begin, row_end) of the pair triangle -> (edges[edge_cap] int64 keys rank_lo << 32 | rank_hi,
+    unused slots -1; status[1] int32), on the device (first half of bf_nms3d, for the row-sharded NMS)."""
+    dev = corners.device
+    n = corners.shape[0]
+    edges = torch.empty(edge_cap, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    h = handle(dev)
+    _call(h, "bf_nms3d_edges", h.lib.bf_nms3d_edges, h.h, ptr(corners), n, ptr(order), int(row_begin), int(row_end), float(iou_threshold),
+          int(mode), ptr(edges), int(edge_cap), ptr(status), h.stream())
+    return edges, status
+
+
+def nms3d_greedy(edges, centers, order, init_id, poses, fusion_list, fusion_len, fusion_flag, translation_gap: float,
+                 rotation_gap: float, center_gap: float = 0.5):
+    """Greedy scan of nms_3d + BoxManager.record over an edge list (second half of bf_nms3d) -> (keep, success, status)."""
+    dev = centers.device
+    n = centers.shape[0]
+    keep = torch.empty(n, dtype=torch.int32, device=dev)
+    success = torch.empty(n, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    h = handle(dev)
+    _call(h, "bf_nms3d_greedy", h.lib.bf_nms3d_greedy, h.h, ptr(edges), int(edges.shape[0]), ptr(centers), n, ptr(order), ptr(init_id),
+          ptr(poses), ptr(fusion_list), ptr(fusion_len), ptr(fusion_flag), float(translation_gap), float(rotation_gap),
+          float(center_gap), ptr(keep), ptr(success), ptr(status), h.stream())
     return keep, success, status
 
 

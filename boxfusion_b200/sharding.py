@@ -101,3 +101,44 @@ def iou3d_matrix_sharded(cornersA: torch.Tensor, cornersB: torch.Tensor, mode: i
     else:
         local = torch.zeros((0, cornersB.shape[0]), dtype=torch.float64, device=cornersB.device)
     return gather_blocks(local, M, group)
+
+
+def pair_row_ranges(n: int, world: int):
+    """Row blocks [lo, hi) of the pair triangle {(a, b): a < b < n} with (nearly) equal pair counts: row a has n-1-a pairs."""
+    total = n * (n - 1) // 2
+    bounds, a, acc = [0], 0, 0
+    for r in range(1, world):
+        target = total * r // world
+        while a < n and acc + (n - 1 - a) <= target:
+            acc += n - 1 - a
+            a += 1
+        bounds.append(a)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def nms3d_sharded(corners, centers, order, init_id, poses, fusion_list, fusion_len, fusion_flag, iou_threshold, translation_gap,
+                  rotation_gap, center_gap=0.5, mode=0, edges_fn=None, greedy_fn=None, group=None):
+    """nms_3d + BoxManager.record (instances.py:22-101, box_manager.py:40-88) with the IoU work sharded by rows of the pair
+    triangle (SURVEY.md section 8(e) axis 3): every rank finds the over-threshold pairs of its rows (bf_nms3d_edges), ONE
+    all_gather of the edge lists - 8 bytes per over-threshold pair, 64 KB at most - and every rank runs the greedy scan with
+    record() over the same concatenated list (bf_nms3d_greedy), so the fusion lists end up identical everywhere.
+    Returns (keep, success, status) like ops.nms3d.  The dense [N, N] IoU matrix is never formed or moved."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = corners.shape[0]
+    lo, hi = pair_row_ranges(n, world)[rank]
+    if edges_fn is None or greedy_fn is None:
+        from . import ops
+        cap = ops.EDGE_CAP // world
+        edges_fn = edges_fn or (lambda a, b: ops.nms3d_edges(corners, order, a, b, iou_threshold, mode, edge_cap=cap))
+        greedy_fn = greedy_fn or (lambda e: ops.nms3d_greedy(e, centers, order, init_id, poses, fusion_list, fusion_len, fusion_flag,
+                                                             translation_gap, rotation_gap, center_gap))
+    local, st_local = edges_fn(lo, hi)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    keep, success, status = greedy_fn(torch.cat(parts))
+    if st_local is not None:
+        st = st_local.clone()
+        dist.all_reduce(st, op=dist.ReduceOp.MIN, group=group)          # BF_ERR_* are negative: any rank's overflow reaches everybody
+        status = torch.minimum(status, st.to(status.device))
+    return keep, success, status

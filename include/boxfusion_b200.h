@@ -102,6 +102,19 @@ int bf_nms3d(bf_handle* h, const float* corners /*[N,8,3]*/, const float* center
              double iou_threshold, float translation_gap, float rotation_gap_deg, float center_gap, int mode,
              int32_t* keep, int32_t* success, int32_t* status, void* stream);
 
+/* The two halves of bf_nms3d as separate entries, for the row-sharded NMS of several GPUs (SURVEY.md section 8(e) axis 3):
+ * bf_nms3d_edges finds the over-threshold pairs (a, b), a in [row_begin, row_end), a < b, of the pair triangle and writes one
+ * key (rank_lo << 32 | rank_hi, ranks in score order) per pair into edges[0..edge_cap) (unused slots = ~0; more pairs than
+ * edge_cap <= 8192 -> status BF_ERR_CAPACITY); the ranks all_gather their edge lists (a few KB) and every rank runs
+ * bf_nms3d_greedy - the serial greedy scan of nms_3d plus record() - over the concatenation (n_slots <= 8192 slots, empty
+ * ones ignored).  Together they compute exactly bf_nms3d. */
+int bf_nms3d_edges(bf_handle* h, const float* corners /*[N,8,3]*/, int N, const int32_t* order, int row_begin, int row_end,
+                   double iou_threshold, int mode, unsigned long long* edges /*[edge_cap]*/, int edge_cap, int32_t* status, void* stream);
+int bf_nms3d_greedy(bf_handle* h, const unsigned long long* edges /*[n_slots]*/, int n_slots, const float* centers /*[N,3]*/, int N,
+                    const int32_t* order, const int32_t* init_id, const float* poses, int32_t* fusion_list, int32_t* fusion_len,
+                    int32_t* fusion_flag, float translation_gap, float rotation_gap_deg, float center_gap,
+                    int32_t* keep, int32_t* success, int32_t* status, void* stream);
+
 /* ---- A9-A12  correspondence_association core (instances.py:446-483, 643-717; box_manager.py:90-129)
  * For each of n_small detections (2-D boxes det_xyxy, float32) project the G candidate map boxes
  * (corners, float32) with pose_inv (row-major 4x4 float32, already inverted by the caller exactly as

@@ -252,6 +252,45 @@ def test_nms_dense_fallback_many_heads(monkeypatch):
     assert got[2] == ref[2] and got[3] == ref[3] and np.array_equal(got[4], ref[4])
 
 
+def test_nms_split_into_edges_and_greedy_equals_nms3d():
+    """bf_nms3d_edges over row blocks of the pair triangle + bf_nms3d_greedy over the concatenated (padded) edge lists == bf_nms3d
+    (the decomposition the multi-GPU NMS uses, boxfusion_b200/sharding.py::nms3d_sharded)."""
+    from boxfusion_b200.sharding import pair_row_ranges
+    t, R, s, lists, flags, poses, init_id = _nms_case(300, 80, 11)
+    n = t.shape[0]
+    corners, centers = ops.box_corners(torch.from_numpy(t).cuda(), torch.from_numpy(R).cuda(), want_centers=True)
+    sc = torch.from_numpy(s).cuda()
+    order = ops.score_order(sc)
+    iid = torch.from_numpy(init_id).to(torch.int32).cuda()
+    po = torch.from_numpy(poses).cuda().reshape(-1, 16)
+    cfg = make_cfg("ca1m", pst_path=make_pst(32))
+
+    def fresh():
+        bm = api.BoxManager(cfg)
+        bm.fusion_list = [list(l) for l in lists]
+        bm.fusion_flag = list(flags)
+        fl, ln, fg = bm.pack_lists(n)
+        return torch.from_numpy(fl).cuda(), torch.from_numpy(ln).cuda(), torch.from_numpy(fg).cuda()
+    fl0, ln0, fg0 = fresh()
+    keep0, succ0, st0 = ops.nms3d(corners, centers, order, iid, po, fl0, ln0, fg0, 0.1, 0.8, 30.0, 0.5)
+    assert int(st0.item()) == 0 and int(succ0.sum().item()) > 20
+    for world in (1, 2, 3, 8):
+        parts, total = [], 0
+        for lo, hi in pair_row_ranges(n, world):
+            e, st = ops.nms3d_edges(corners, order, lo, hi, 0.1, edge_cap=ops.EDGE_CAP // world)
+            assert int(st.item()) == 0
+            total += int((e != -1).sum().item())
+            parts.append(e)
+        fl1, ln1, fg1 = fresh()
+        keep1, succ1, st1 = ops.nms3d_greedy(torch.cat(parts), centers, order, iid, po, fl1, ln1, fg1, 0.8, 30.0, 0.5)
+        assert int(st1.item()) == 0 and total > 50
+        assert torch.equal(keep0, keep1) and torch.equal(succ0, succ1), world
+        assert torch.equal(ln0, ln1) and torch.equal(fg0, fg1) and torch.equal(fl0, fl1), world
+    # an edge list that does not fit its share is reported, not truncated silently
+    _, st = ops.nms3d_edges(corners, order, 0, n, 0.1, edge_cap=8)
+    assert int(st.item()) == -3
+
+
 def test_nms_single_box_quirk():
     case = _nms_case(1, 0, 5)
     cfg = make_cfg("ca1m", pst_path=make_pst(32))

@@ -138,3 +138,70 @@ def test_two_rank_box_sharded_refine_and_row_sharded_iou(tmp_path):
     cb = port.GeneralInstance3DBoxes(torch.from_numpy(prob["tensor"][:, 1]), torch.from_numpy(prob["R"][:, 1])).corners.numpy()
     exp = np.stack([port.calculate_obb_iou(x, cb) for x in ca])
     assert got["iou"].shape == (B, B) and np.array_equal(got["iou"], exp)
+
+
+# ---- row-sharded NMS: edge lists gathered, greedy scan replicated (SURVEY 8(e) axis 3) ------------------------------------
+def _nms_inputs():
+    from boxfusion_b200.synthetic import map_and_detections
+    from oracle import port
+    (mt, mR, ms), (dt, dR, ds) = map_and_detections(40, 14, seed=6, tilt_noise=0.01)
+    t, R, s = np.concatenate([mt, dt]), np.concatenate([mR, dR]), np.concatenate([ms, ds])
+    corners = port.GeneralInstance3DBoxes(torch.from_numpy(t), torch.from_numpy(R)).corners.numpy()
+    order = np.argsort(-s, kind="stable")
+    rank = np.empty_like(order); rank[order] = np.arange(len(order))
+    return corners, s, rank
+
+
+def _edges_of_rows(corners, rank, lo, hi, thr=0.1, cap=64):
+    """the contract of ops.nms3d_edges served by the CPU oracle: keys rank_lo << 32 | rank_hi, empty slots -1"""
+    from oracle import port
+    port.IOU_BACKEND = "c"
+    keys = []
+    for a in range(lo, hi):
+        if a + 1 < len(corners):
+            iou = port.calculate_obb_iou(corners[a], corners[a + 1:])
+            for j in np.nonzero(iou > thr)[0]:
+                b = a + 1 + int(j)
+                r0, r1 = sorted((int(rank[a]), int(rank[b])))
+                keys.append((r0 << 32) | r1)
+    out = np.full(cap, -1, dtype=np.int64)
+    out[: len(keys)] = keys
+    return torch.from_numpy(out), torch.zeros(1, dtype=torch.int32)
+
+
+def _worker_nms(rank, world, port_no, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from boxfusion_b200.sharding import nms3d_sharded
+    corners, s, rk = _nms_inputs()
+    got = {}
+
+    def greedy(edges):                                  # what reaches the replicated greedy scan is the thing under test
+        got["edges"] = edges.numpy().copy()
+        n = len(corners)
+        return torch.zeros(n, dtype=torch.int32), torch.zeros(n, dtype=torch.int32), torch.zeros(1, dtype=torch.int32)
+    nms3d_sharded(torch.from_numpy(corners), None, None, None, None, None, None, None, 0.1, 0.8, 30.0,
+                  edges_fn=lambda lo, hi: _edges_of_rows(corners, rk, lo, hi), greedy_fn=greedy)
+    np.save(os.path.join(out_dir, f"edges{rank}.npy"), got["edges"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_sharded_nms_edges(tmp_path):
+    from boxfusion_b200.sharding import pair_row_ranges
+    for n, world in ((54, 2), (4352, 8), (5, 8), (1, 2), (0, 2)):
+        rr = pair_row_ranges(n, world)
+        assert rr[0][0] == 0 and rr[-1][1] == n and all(a[1] == b[0] for a, b in zip(rr, rr[1:]))
+        pairs = [sum(n - 1 - a for a in range(lo, hi)) for lo, hi in rr]
+        assert sum(pairs) == n * (n - 1) // 2
+        if n == 4352:
+            assert max(pairs) - min(pairs) <= 2 * n              # balanced by pair count (to within two rows), not by row count
+    port_no = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_nms, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    corners, s, rk = _nms_inputs()
+    full, _ = _edges_of_rows(corners, rk, 0, len(corners), cap=128)
+    want = np.sort(full.numpy()[full.numpy() >= 0])
+    for r in range(2):                                          # every rank feeds the same edge set to its greedy scan
+        e = np.load(tmp_path / f"edges{r}.npy")
+        assert e.shape == (128,) and np.array_equal(np.sort(e[e >= 0]), want) and len(want) > 5
