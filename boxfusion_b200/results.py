@@ -31,7 +31,10 @@ def map_corners(all_pred_box) -> np.ndarray:
     b = all_pred_box.pred_boxes_3d
     if len(b) == 0:
         return np.zeros((0, 8, 3), dtype=np.float32)
-    return ops.to_host(ops.box_corners(b.tensor, b.R))
+    c = ops.to_host(ops.box_corners(b.tensor, b.R))
+    # the reference's corners are the transpose(1, 2) VIEW of a [N,3,8] tensor (boxes.py:767-778), so every [8,3] array it
+    # pickles is Fortran-ordered; same memory layout here -> the pickles are byte-identical, not just equal in value
+    return np.ascontiguousarray(c.transpose(0, 2, 1)).transpose(0, 2, 1)
 
 
 def global_save_list(all_pred_box, dataset: str = "CA1M") -> list:

@@ -32,3 +32,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _restore_oracle_backend():
+    """Tests pick the oracle's IoU backend (scipy/Qhull like the reference, or its C restatement) by assigning the module
+    global; put it back so that no test depends on the order they run in."""
+    from oracle import port
+    saved = port.IOU_BACKEND
+    yield
+    port.IOU_BACKEND = saved
