@@ -481,9 +481,11 @@ int bf_refine_run(bf_handle* h, const float* pst, int P, const float* per_xyzlhw
         variant = ((double)B * (double)items >= (double)h->sm_count * 8192.0) ? 2 : 1;
         bestT = 256;
         const long long slots = (long long)h->sm_count * (variant == 2 ? 4 : 3);
-        // about two waves of CTAs: boxes that stop early leave their slots to the second wave (measured on C4, round 2:
-        // clusters of 2 / 4 / 8 / 16 -> 74 / 63 / 59 / 62 ms forced, 46 / 34 / 31 / 30 ms with early stop)
-        while (bestC < 16 && (long long)B * bestC * 2 <= 2 * slots) bestC *= 2;
+        // saturated: about two waves of CTAs - boxes that stop early leave their slots to the second wave (measured on C4,
+        // round 2: clusters of 2 / 4 / 8 / 16 -> 74 / 63 / 59 / 62 ms forced, 46 / 34 / 31 / 30 ms with early stop);
+        // mid regime: fill the resident slots once (C1: clusters of 8 -> 0.64 ms, of 16 -> 0.75 ms)
+        const long long fill = (variant == 2) ? 2 * slots : slots + slots / 8;
+        while (bestC < 16 && (long long)B * bestC * 2 <= fill) bestC *= 2;
         best_cost = 0.0;
     }
     if (!saturated && !persistent && h->refine_concurrent) {       // BF_OPT_REFINE_CONCURRENT: leave room for the other streams' kernels

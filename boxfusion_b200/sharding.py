@@ -134,11 +134,12 @@ def nms3d_sharded(corners, centers, order, init_id, poses, fusion_list, fusion_l
         greedy_fn = greedy_fn or (lambda e: ops.nms3d_greedy(e, centers, order, init_id, poses, fusion_list, fusion_len, fusion_flag,
                                                              translation_gap, rotation_gap, center_gap))
     local, st_local = edges_fn(lo, hi)
-    parts = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    keep, success, status = greedy_fn(torch.cat(parts))
-    if st_local is not None:
-        st = st_local.clone()
-        dist.all_reduce(st, op=dist.ReduceOp.MIN, group=group)          # BF_ERR_* are negative: any rank's overflow reaches everybody
-        status = torch.minimum(status, st.to(status.device))
+    # one all_gather carries the edge slots and, in one extra slot, the rank's status word (BF_ERR_* are negative)
+    st_word = st_local.to(torch.int64).reshape(1) if st_local is not None else torch.zeros(1, dtype=torch.int64, device=local.device)
+    buf = torch.cat([local.reshape(-1), st_word.to(local.device)])
+    out = torch.empty(world * buf.numel(), dtype=buf.dtype, device=buf.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.view(world, -1)
+    keep, success, status = greedy_fn(out[:, :-1].reshape(-1).contiguous())
+    status = torch.minimum(status, out[:, -1].min().to(torch.int32).reshape(1).to(status.device))   # any rank's overflow reaches everybody
     return keep, success, status
