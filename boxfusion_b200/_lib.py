@@ -109,6 +109,9 @@ PROTOTYPES = {
     "bf_engine_set_counts": (_i32, [_vp, _i32, _i32, _vp]),
     "bf_engine_read_state": (_i32, [_vp, _ESP, _vp]),
     "bf_engine_read_flags": (_i32, [_vp, _vp, _vp, _i32, _ESP, _vp]),
+    "bf_engine_run_ahead": (_i32, [_vp, _i32, _vp]),
+    "bf_engine_wait_flags": (_i32, [_vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "bf_engine_rollback": (_i32, [_vp, _vp]),
     "bf_engine_read_i32": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "bf_engine_pointers": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "bf_engine_launch_counts": (_i32, [_vp, ctypes.POINTER(ctypes.c_int32)]),

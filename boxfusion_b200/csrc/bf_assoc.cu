@@ -165,6 +165,19 @@ bf_greedy_kernel(const unsigned long long* __restrict__ edges, const unsigned lo
         if (valid) atomicAdd(&s_E, valid);
         __syncthreads();
         E_sparse = s_E;                                        // real edges (gathered lists carry empty slots)
+        if (n2 <= T) {
+            // a keyframe has a few dozen edges: rank every key by counting the smaller ones (keys are unique; empty slots
+            // are all ~0 and rank by position) - two block barriers instead of one per stage of a sorting network
+            unsigned long long key = ~0ULL;
+            int rnk = 0;
+            if (tid < n2) {
+                key = s_keys[tid];
+                for (int j = 0; j < n2; ++j) { const unsigned long long o = s_keys[j]; rnk += (o < key || (o == key && j < tid)) ? 1 : 0; }
+            }
+            __syncthreads();
+            if (tid < n2) s_keys[rnk] = key;
+            __syncthreads();
+        } else
         for (int k = 2; k <= n2; k <<= 1)                      // bitonic sort, ascending
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int i = tid; i < n2; i += T) {
@@ -236,6 +249,7 @@ bf_greedy_kernel(const unsigned long long* __restrict__ edges, const unsigned lo
         const bool rem = (remaining[r >> 5] >> (r & 31)) & 1u;
         const int k = ctx.keep[i];
         ctx.keep[i] = (k == 1) ? 1 : ((k == -1) ? 0 : (rem ? 1 : 0));
+        if (ctx.valid_num && success[i]) ctx.valid_num[i] += 1.f;          // instances.py:72-73
     }
 }
 
@@ -246,7 +260,7 @@ bf_greedy_kernel(const unsigned long long* __restrict__ edges, const unsigned lo
 int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_dimref Nd, const int32_t* order, int32_t* rank_or_null,
                  const int32_t* init_id, const float* poses, int32_t* fusion_list, int32_t* fusion_len, int32_t* fusion_flag,
                  double iou_threshold, float translation_gap, float rotation_gap_deg, float center_gap, int mode,
-                 int32_t* keep, int32_t* success, int32_t* status, cudaStream_t st) {
+                 int32_t* keep, int32_t* success, int32_t* status, float* valid_num_or_null, cudaStream_t st) {
     const int N = Nd.host;
     const int W = (N + 31) / 32;
     const bool dense = N <= BF_DENSE_MASK_MAX_N;
@@ -292,6 +306,7 @@ int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_di
     ctx.order = order; ctx.init_id = init_id; ctx.poses = poses; ctx.centers = centers; ctx.fl = fusion_list;
     ctx.flen = fusion_len; ctx.fflag = fusion_flag; ctx.keep = keep; ctx.status = status;
     ctx.translation_gap = translation_gap; ctx.rotation_gap = rotation_gap_deg; ctx.center_gap = center_gap;
+    ctx.valid_num = valid_num_or_null;
     // sorted edge list in shared memory (keys + remaining bit set + live flags); the dense path needs the bit set only
     const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
     BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
@@ -353,6 +368,7 @@ extern "C" int bf_nms3d_greedy(bf_handle* h, const unsigned long long* edges, in
     ctx.order = order; ctx.init_id = init_id; ctx.poses = poses; ctx.centers = centers; ctx.fl = fusion_list;
     ctx.flen = fusion_len; ctx.fflag = fusion_flag; ctx.keep = keep; ctx.status = status;
     ctx.translation_gap = translation_gap; ctx.rotation_gap = rotation_gap_deg; ctx.center_gap = center_gap;
+    ctx.valid_num = nullptr;
     const int W = (N + 31) / 32;
     const size_t smem_e = sizeof(unsigned long long) * BF_EDGE_CAP + sizeof(uint32_t) * (size_t)W + BF_EDGE_CAP + 16;
     BF_CUDA(h, cudaFuncSetAttribute(bf_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
@@ -372,7 +388,7 @@ extern "C" int bf_nms3d(bf_handle* h, const float* corners, const float* centers
         !success || !status)
         return bf_fail(h, BF_ERR_INVALID_ARG, "bf_nms3d", "null pointer");
     return bf_nms3d_run(h, corners, centers, bf_dim_host(N), order, nullptr, init_id, poses, fusion_list, fusion_len, fusion_flag,
-                        iou_threshold, translation_gap, rotation_gap_deg, center_gap, mode, keep, success, status, (cudaStream_t)stream);
+                        iou_threshold, translation_gap, rotation_gap_deg, center_gap, mode, keep, success, status, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

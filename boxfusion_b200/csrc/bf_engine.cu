@@ -35,9 +35,13 @@ struct bf_engine {
     size_t in_floats;
     // graphs
     cudaStream_t cap_stream;
-    cudaGraphExec_t exec[8];          // one per phase bit + [7] the whole keyframe
+    cudaGraphExec_t exec[9];          // one per phase bit, [7] the whole keyframe, [8] everything after the correspondence phase
     int have_graph;
-    int launches[8];
+    int launches[9];
+    // run-ahead (the reference-shaped API): rollback snapshot of the state right after the NMS phase, pinned flag buffers
+    uint32_t* snapshot;               // [ncap * SNAP_ROW + 2 * ncap + 64] words, allocated on first use
+    int32_t* hflags[2];               // pinned host: keep[ncap], success[ncap], state[32]
+    cudaEvent_t flag_evt[2];
     char err[512];
 };
 
@@ -217,8 +221,7 @@ bf_engine_corr_kernel(bf_engine_ctx c) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_any_new = 0; s_any_small = 0; }
     __syncthreads();
-    // valid_num += 1 for every head that suppressed something (instances.py:72-73)
-    for (int i = tid; i < N_glo + n; i += T) if (success[i]) mp.valid[i] += 1.f;
+    // (valid_num += 1 for every head that suppressed something, instances.py:72-73, was applied by the NMS phase)
     for (int j = tid; j < n; j += T) {
         if (keep[N_glo + j]) {
             s_any_new = 1;
@@ -265,7 +268,7 @@ bf_engine_corr_kernel(bf_engine_ctx c) {
     __syncthreads();
     bf_record_ctx rc;
     rc.order = nullptr; rc.init_id = mp.init_id; rc.poses = sposes; rc.centers = nullptr; rc.fl = mp.fl; rc.flen = mp.flen;
-    rc.fflag = c.fflag; rc.keep = keep; rc.status = &st->status[1];
+    rc.fflag = c.fflag; rc.keep = keep; rc.status = &st->status[1]; rc.valid_num = nullptr;
     rc.translation_gap = c.tgap; rc.rotation_gap = c.rgap; rc.center_gap = 0.f;
     // small new boxes in index order; scoring in parallel, decision by thread 0 (:446-483)
     for (int j = 0; j < n; ++j) {
@@ -594,7 +597,7 @@ static int e_ph_nms(bf_engine* e, cudaStream_t st, int* L) {
     E_SUB(e, bf_score_order_run(h, mp.scores, Nd, e->order, e->rank, st));
     E_SUB(e, bf_nms3d_run(h, e->corners, e->centers, Nd, e->order, e->rank, mp.init_id, e->bufs.store.pose, mp.fl, mp.flen,
                           e->bufs.fusion_flag, g.nms_threshold, g.translation_gap, g.rotation_gap, g.center_gap, g.iou_mode,
-                          e->keep, e->success, &e->state->status[0], st));
+                          e->keep, e->success, &e->state->status[0], mp.valid, st));
     (void)c;
     // corners, order, planes, pairs, count, greedy
     *L = 6;
@@ -696,7 +699,9 @@ extern "C" void bf_engine_destroy(bf_engine* e) {
     if (!e) return;
     if (e->h) cudaSetDevice(e->h->device);
     cudaDeviceSynchronize();
-    for (int p = 0; p < PH_COUNT + 1; ++p) if (e->exec[p]) cudaGraphExecDestroy(e->exec[p]);
+    for (int p = 0; p < PH_COUNT + 2; ++p) if (e->exec[p]) cudaGraphExecDestroy(e->exec[p]);
+    if (e->snapshot) cudaFree(e->snapshot);
+    for (int i = 0; i < 2; ++i) { if (e->hflags[i]) cudaFreeHost(e->hflags[i]); if (e->flag_evt[i]) cudaEventDestroy(e->flag_evt[i]); }
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     for (int i = 0; i < bf_engine::RING; ++i) { if (e->stage[i]) cudaFreeHost(e->stage[i]); if (e->stage_evt[i]) cudaEventDestroy(e->stage_evt[i]); }
     void* bufs[] = {e->in_dev, e->state, e->keep, e->success, e->todo, e->offsets, e->view_index, e->order, e->rank, e->src, e->snap,
@@ -748,6 +753,7 @@ extern "C" int bf_engine_create(int device, const bf_engine_cfg* cfg, const bf_e
         for (int p = 0; p < PH_COUNT; ++p)
             if ((rc = e_capture_one(e, 1 << p, &e->exec[p], &e->launches[p]))) return rc;
         if ((rc = e_capture_one(e, e_full_mask(e), &e->exec[PH_COUNT], &e->launches[PH_COUNT]))) return rc;
+        if ((rc = e_capture_one(e, e_full_mask(e) & ~((1 << PH_INGEST) | (1 << PH_NMS) | (1 << PH_CORR)), &e->exec[PH_COUNT + 1], &e->launches[PH_COUNT + 1]))) return rc;
         e->have_graph = 1;
     } else {
         // launch counts of the eager sequences (same kernels)
@@ -773,6 +779,7 @@ extern "C" int bf_engine_reset(bf_engine* e, void* stream) {
 static int e_run(bf_engine* e, int phases, cudaStream_t st) {
     if (!e->have_graph) return e_issue(e, phases, st, nullptr);
     if (phases == e_full_mask(e)) { E_CUDA(e, cudaGraphLaunch(e->exec[PH_COUNT], st)); return BF_OK; }
+    if (phases == (e_full_mask(e) & ~((1 << PH_INGEST) | (1 << PH_NMS) | (1 << PH_CORR)))) { E_CUDA(e, cudaGraphLaunch(e->exec[PH_COUNT + 1], st)); return BF_OK; }
     for (int p = 0; p < PH_COUNT; ++p)
         if (phases & (1 << p)) E_CUDA(e, cudaGraphLaunch(e->exec[p], st));
     return BF_OK;
@@ -840,6 +847,98 @@ extern "C" int bf_engine_set_counts(bf_engine* e, int N, int M, void* stream) {
     bf_device_guard guard(e->h);
     bf_engine_set_counts_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e_ctx(e), N, M);
     E_LAUNCH_CHECK(e, "bf_engine_set_counts_kernel");
+    return BF_OK;
+}
+
+// ---- run-ahead for the reference-shaped API -------------------------------------------------------------------------------------
+// spatial_association has to hand the keep / success indices to the caller, but nothing the caller does with them feeds back
+// into the keyframe: bf_engine_run_ahead issues the NMS phase, an asynchronous copy of the flags to pinned memory, a snapshot
+// of everything the later phases overwrite, the correspondence phase, a second copy of the keep flags, and the rest of the
+// keyframe - so the GPU refines while the host is still inside the caller's Python.  If the caller then strays from demo.py's
+// sequence, bf_engine_rollback restores the state of right after the NMS phase and the phases are re-issued one by one:
+// running ahead is invisible.
+#define BF_SNAP_ROW 90                 // words per map row: 6 + 9 + 1 + 4 + 2 + 16 + 16 + 1 + 1 + 1 + 32 + 1
+__global__ void bf_engine_snapshot_kernel(bf_engine_ctx c, uint32_t* __restrict__ snap, int restore) {
+    bf_engine_state* st = c.st;
+    uint32_t* s_keep = snap + (size_t)c.ncap * BF_SNAP_ROW;
+    uint32_t* s_flag = s_keep + c.ncap;
+    uint32_t* s_state = s_flag + c.ncap;                  // 32 words of state, then the fused count
+    const int N = restore ? ((const bf_engine_state*)s_state)->Nall : st->Nall;
+    const bf_map_buffers& mp = c.map[0];
+    const int t = threadIdx.x;                            // 64 threads per row
+    for (int k = blockIdx.x; k < N; k += gridDim.x) {
+        uint32_t* row = snap + (size_t)k * BF_SNAP_ROW;
+        const size_t d = (size_t)k;
+#define BF_SNAP_FIELD(ptr, width, off)                                                                              \
+        if (t < (width)) { uint32_t* q = (uint32_t*)(ptr) + (width) * d + t; if (restore) *q = row[(off) + t]; else row[(off) + t] = *q; }
+        BF_SNAP_FIELD(mp.tensor, 6, 0) BF_SNAP_FIELD(mp.R, 9, 6) BF_SNAP_FIELD(mp.scores, 1, 15) BF_SNAP_FIELD(mp.box2d, 4, 16)
+        BF_SNAP_FIELD(mp.projxy, 2, 20) BF_SNAP_FIELD(mp.pose, 16, 22) BF_SNAP_FIELD(mp.uv, 16, 38) BF_SNAP_FIELD(mp.valid, 1, 54)
+        BF_SNAP_FIELD(mp.init_id, 1, 55) BF_SNAP_FIELD(mp.frame_id, 1, 56) BF_SNAP_FIELD(mp.fl, BF_FUSION_CAP, 57)
+        BF_SNAP_FIELD(mp.flen, 1, 89)
+#undef BF_SNAP_FIELD
+        if (t == 63) {
+            if (restore) { c.keep[k] = (int32_t)s_keep[k]; c.fflag[k] = (int32_t)s_flag[k]; }
+            else { s_keep[k] = (uint32_t)c.keep[k]; s_flag[k] = (uint32_t)c.fflag[k]; }
+        }
+    }
+    if (blockIdx.x == 0 && t < 32) {
+        if (restore) ((uint32_t*)st)[t] = s_state[t]; else s_state[t] = ((const uint32_t*)st)[t];
+        if (t == 0) { if (restore) c.fused.count[0] = (int32_t)s_state[32]; else s_state[32] = (uint32_t)c.fused.count[0]; }
+    }
+}
+
+static int e_flags_async(bf_engine* e, int slot, int rows, int with_success, cudaStream_t st) {
+    int32_t* hp = e->hflags[slot];
+    const size_t ncap = (size_t)e->cfg.map_capacity;
+    if (rows) E_CUDA(e, cudaMemcpyAsync(hp, e->keep, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    if (rows && with_success) E_CUDA(e, cudaMemcpyAsync(hp + ncap, e->success, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    E_CUDA(e, cudaMemcpyAsync(hp + 2 * ncap, e->state, sizeof(bf_engine_state), cudaMemcpyDeviceToHost, st));
+    E_CUDA(e, cudaEventRecord(e->flag_evt[slot], st));
+    return BF_OK;
+}
+
+static int e_tail_mask(const bf_engine* e) { return e_full_mask(e) & ~((1 << PH_INGEST) | (1 << PH_NMS) | (1 << PH_CORR)); }
+
+extern "C" int bf_engine_run_ahead(bf_engine* e, int rows, void* stream) {
+    if (!e || rows < 0 || rows > e->cfg.map_capacity) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_run_ahead", "bad argument");
+    bf_device_guard guard(e->h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ncap = (size_t)e->cfg.map_capacity;
+    if (!e->snapshot) {
+        E_CUDA(e, cudaMalloc((void**)&e->snapshot, sizeof(uint32_t) * (ncap * BF_SNAP_ROW + 2 * ncap + 64)));
+        for (int i = 0; i < 2; ++i) {
+            E_CUDA(e, cudaMallocHost((void**)&e->hflags[i], sizeof(int32_t) * (2 * ncap + 32)));
+            E_CUDA(e, cudaEventCreateWithFlags(&e->flag_evt[i], cudaEventDisableTiming));
+        }
+    }
+    int rc;
+    if ((rc = e_run(e, 1 << PH_NMS, st))) return rc;
+    if ((rc = e_flags_async(e, 0, rows, 1, st))) return rc;
+    const int sgrid = rows < 1 ? 1 : (rows < 1024 ? rows : 1024);
+    bf_engine_snapshot_kernel<<<sgrid, 64, 0, st>>>(e_ctx(e), e->snapshot, 0);
+    E_LAUNCH_CHECK(e, "bf_engine_snapshot_kernel");
+    if ((rc = e_run(e, 1 << PH_CORR, st))) return rc;
+    if ((rc = e_flags_async(e, 1, rows, 0, st))) return rc;
+    return e_run(e, e_tail_mask(e), st);
+}
+
+extern "C" int bf_engine_wait_flags(bf_engine* e, int slot, int32_t** keep, int32_t** success, bf_engine_state** state) {
+    if (!e || slot < 0 || slot > 1 || !e->hflags[slot]) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_wait_flags", "bad argument");
+    bf_device_guard guard(e->h);
+    E_CUDA(e, cudaEventSynchronize(e->flag_evt[slot]));
+    const size_t ncap = (size_t)e->cfg.map_capacity;
+    if (keep) *keep = e->hflags[slot];
+    if (success) *success = e->hflags[slot] + ncap;
+    if (state) *state = (bf_engine_state*)(e->hflags[slot] + 2 * ncap);
+    return BF_OK;
+}
+
+extern "C" int bf_engine_rollback(bf_engine* e, void* stream) {
+    if (!e || !e->snapshot) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_rollback", "nothing to roll back");
+    bf_device_guard guard(e->h);
+    const int g = e->cfg.map_capacity < 1024 ? e->cfg.map_capacity : 1024;
+    bf_engine_snapshot_kernel<<<g, 64, 0, (cudaStream_t)stream>>>(e_ctx(e), e->snapshot, 1);
+    E_LAUNCH_CHECK(e, "bf_engine_snapshot_kernel");
     return BF_OK;
 }
 

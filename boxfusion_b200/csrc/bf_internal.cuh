@@ -9,6 +9,7 @@ struct bf_record_ctx {
     const float* centers;                 // nullptr: record_corr (no centre-distance term, box_manager.py:100-102)
     int32_t* fl; int32_t* flen; int32_t* fflag; int32_t* keep; int32_t* status;
     float translation_gap, rotation_gap, center_gap;
+    float* valid_num;                     // optional: `valid_num[i] += 1` for every head that suppressed something (instances.py:72-73)
 };
 
 // K1 (bf_iou3d.cu)
@@ -22,7 +23,7 @@ int bf_score_order_run(bf_handle* h, const float* scores, bf_dimref Nd, int32_t*
 int bf_nms3d_run(bf_handle* h, const float* corners, const float* centers, bf_dimref Nd, const int32_t* order, int32_t* rank_or_null,
                  const int32_t* init_id, const float* poses, int32_t* fusion_list, int32_t* fusion_len, int32_t* fusion_flag,
                  double iou_threshold, float translation_gap, float rotation_gap_deg, float center_gap, int mode,
-                 int32_t* keep, int32_t* success, int32_t* status, cudaStream_t st);
+                 int32_t* keep, int32_t* success, int32_t* status, float* valid_num_or_null, cudaStream_t st);
 
 // geometry (bf_geometry.cu)
 int bf_box_corners_run(bf_handle* h, const float* xyzlhw, const float* R, bf_dimref Nd, float* corners, float* centers, cudaStream_t st);

@@ -116,9 +116,12 @@ class FusionEngine:
                 self.lib.bf_engine_destroy(e)
             raise RuntimeError(f"bf_engine_create failed ({rc}): {msg}")
         self.e = e
-        counts = (ctypes.c_int32 * 8)()
+        counts = (ctypes.c_int32 * 9)()
         self.lib.bf_engine_launch_counts(e, counts)
         self.launch_counts = list(counts)
+        self.full_mask = (_lib.PH_INGEST | _lib.PH_NMS | _lib.PH_CORR | _lib.PH_COMPACT | (_lib.PH_VALID if ec.check_valid else 0) |
+                          (_lib.PH_FUSE if ec.use_fusion else 0) | _lib.PH_FINISH)
+        self.fuses_finish = bool(ec.use_fusion and use_graph)       # bf_engine_apply closes the keyframe itself in the captured tail
         self._state = EngineState()
         self._state_fresh = True          # host copy of the counters equals the device's
         self.M = 0                        # observations (= box_count = len(per_frame_ins) = len(fusion_flag)); exact on the host

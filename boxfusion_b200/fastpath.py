@@ -36,6 +36,7 @@ from . import _lib, ops
 from ._lib import KF_HEADER
 
 ENABLED = True                      # module switch (tests compare the two implementations)
+RUN_AHEAD = True                    # queue the rest of the keyframe behind spatial_association (rolled back if the caller strays)
 
 _MAP_NATIVE = ("scores", "pred_boxes", "pred_proj_xy", "pred_boxes_3d", "cam_pose", "frame_id", "init_id", "valid_num", "projected_boxes")
 _STORE_NATIVE = ("scores", "pred_boxes_3d", "cam_pose", "projected_boxes")
@@ -87,6 +88,7 @@ class EngineFields(dict):
 
     def n_rows(self) -> int:
         if self.rows is None:
+            self.sess.settle()
             self.rows = self.sess.engine.N
         return self.rows
 
@@ -190,6 +192,9 @@ class Session:
         self.lists_host = True          # BoxManager's Python lists are current
         self.lists_given = None         # copies of the lists handed to the caller while the device is ahead
         self.pending_new = None         # init_new_predictions(n, M) the engine has not seen yet
+        self.ahead = False              # the engine has run the whole keyframe; the caller is still at `stage` (run-ahead)
+        self.valid_called = False       # the caller has called check_valid_num for the keyframe in flight
+        self.any_new = 1
         self.frame_id = -1
         self._keep = np.zeros(self.engine.ncap, dtype=np.int32)
         self._succ = np.zeros(self.engine.ncap, dtype=np.int32)
@@ -219,6 +224,53 @@ class Session:
         if any(st.status[i] for i in range(8)):
             e.check_status()
 
+    # ---- run-ahead: the engine finishes the keyframe while the caller is still between its calls -----------------------------
+    def _run_ahead(self, rows):
+        e = self.engine
+        rc = e.lib.bf_engine_run_ahead(e.e, rows, self._stp)
+        if rc:
+            e._check(rc, "bf_engine_run_ahead")
+        lc = e.launch_counts
+        ops.Profile.launches += lc[1] + 1 + lc[2] + sum(c for i, c in enumerate(lc[:7]) if i >= 3 and (e.full_mask >> i) & 1) - (1 if e.fuses_finish else 0)
+        e._state_fresh = False
+        self.lists_host = False
+        self.ahead = True
+
+    def _wait_flags(self, slot, rows, want_success):
+        e = self.engine
+        pk, ps, pst = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        rc = e.lib.bf_engine_wait_flags(e.e, slot, ctypes.byref(pk), ctypes.byref(ps), ctypes.byref(pst))
+        if rc:
+            e._check(rc, "bf_engine_wait_flags")
+        I32 = ctypes.POINTER(ctypes.c_int32)
+        keep = np.ctypeslib.as_array(ctypes.cast(pk, I32), shape=(rows,)) if rows else np.zeros(0, np.int32)
+        succ = np.ctypeslib.as_array(ctypes.cast(ps, I32), shape=(rows,)) if (rows and want_success) else None
+        st = ctypes.cast(pst, ctypes.POINTER(_lib.EngineState)).contents
+        ops.Profile.d2h_bytes += 4 * rows * (2 if want_success else 1) + ctypes.sizeof(_lib.EngineState)
+        if any(st.status[i] for i in range(8)):
+            e.check_status()
+        return keep, succ, st
+
+    def settle(self):
+        """Somebody is about to look at engine state (or the caller strayed) while the engine has run ahead of the caller:
+        put the engine where the caller is - restore the snapshot taken right after the NMS phase and re-issue what the
+        caller has called since."""
+        if not self.ahead:
+            return
+        self.ahead = False
+        if self.stage in (Session.IDLE, Session.CAT):
+            return                                                 # the caller has caught up (or nothing was queued)
+        e = self.engine
+        rc = e.lib.bf_engine_rollback(e.e, self._stp)
+        if rc:
+            e._check(rc, "bf_engine_rollback")
+        ops.Profile.launches += 1
+        e._state_fresh = False
+        if self.stage == Session.CORR:
+            self._phase(_lib.PH_CORR | _lib.PH_COMPACT)
+            if self.valid_called:
+                self._phase(_lib.PH_VALID)
+
     def new_container(self, kind, rows, image_size):
         from .instances import Instances3D
         c = Instances3D.__new__(Instances3D)
@@ -241,6 +293,8 @@ class Session:
         fields on the host); leaving the fast path moves them back."""
         from .boxes import GeneralInstance3DBoxes
         e = self.engine
+        if f.kind != "store" or k not in self.store_chunks:
+            self.settle()                                          # engine buffers are about to be read
         if f.kind == "store":
             M, st = f.rows, e.store
             if k == "scores":
@@ -340,11 +394,13 @@ class Session:
             object.__setattr__(c, "_fields", self.fields(kind, rows))
         self.map_c, self.store_c, self.cat_c = A, P, None
         self.stage = Session.IDLE
+        self.ahead, self.valid_called = False, False
         self.lists_host, self.lists_given = True, None
 
     # ---- leaving: export the engine state into plain containers ----------------------------------------------------
     def pull_lists(self, bm):
         """BoxManager's Python lists from the device (the device is ahead while a session runs)."""
+        self.settle()
         e = self.engine
         if self.stage in (Session.CAT, Session.NMS):
             rows = self.N + self.n
@@ -382,14 +438,8 @@ class Session:
             return
         e = self.engine
         self._stp = e._st()
+        self.settle()
         edited = not self.lists_untouched(bm)
-        if self.stage == Session.NMS:                              # the engine applies valid_num += 1 in its correspondence phase
-            succ = np.nonzero(self._succ[: self.N + self.n])[0]
-            if len(succ):
-                with torch.cuda.device(self.dev):
-                    if e.stream is not None:
-                        torch.cuda.current_stream(self.dev).wait_stream(e.stream)
-                    e.map["valid"][torch.from_numpy(succ).to(self.dev)] += 1
         if self.stage == Session.CORR:                             # close the keyframe on the device too (row counters)
             self._phase(_lib.PH_FINISH)
             self.M += self.n
@@ -439,7 +489,12 @@ class Session:
         if A is not self.map_c:
             return None
         if self.stage == Session.CORR:                             # boxfusion() was not called for the last keyframe (cfg / no new box)
-            self._phase(_lib.PH_FINISH)
+            if self.ahead and ((self.use_fusion and self.any_new) or (self.check_valid and self.any_new and not self.valid_called)):
+                self.settle()                                      # the engine fused / dropped what the caller never asked for: undo
+            if self.ahead:
+                self.ahead = False                                 # what ran ahead is exactly what the caller's calls amount to
+            else:
+                self._phase(_lib.PH_FINISH)
             self.engine.M += self.n
             self.engine.count += 1
             self.M += self.n
@@ -492,6 +547,7 @@ class Session:
         e._state_fresh = False
         self.hdr, self.n, self.pred, self.frame_id = hdr, n, B, frame_id
         self.pending_new = None
+        self.valid_called = False
         self.cat_extras = {k: _cat_values(v, fb[k]) for k, v in self.map_extras.items()}
         self.stage = Session.CAT
         self.lists_host, self.lists_given = False, None
@@ -504,22 +560,33 @@ class Session:
         from . import instances as inst_mod
         if float(threshold) != self.key[0] or inst_mod.IOU_MODE != self.iou_mode or cfg_key(self.cfg) != self.key:
             return None
-        self._phase(_lib.PH_NMS)
         rows = self.N + self.n
-        self._read_flags(rows, True)
-        keep = np.nonzero(self._keep[:rows])[0]
-        succ = np.nonzero(self._succ[:rows])[0]
+        if RUN_AHEAD:
+            self._run_ahead(rows)                                  # NMS, flags -> pinned, snapshot, correspondence, flags, rest of the keyframe
+            k, sflags, _ = self._wait_flags(0, rows, True)
+            keep, succ = np.nonzero(k)[0], np.nonzero(sflags)[0]
+        else:
+            self._phase(_lib.PH_NMS)
+            self._read_flags(rows, True)
+            keep = np.nonzero(self._keep[:rows])[0]
+            succ = np.nonzero(self._succ[:rows])[0]
         self.last_keep = keep
         self.stage = Session.NMS
         return keep.tolist(), succ.tolist()
 
     def _after_assoc(self, image_size):
         """PH_CORR, the keep flags, PH_COMPACT -> (container for all_pred_box[keep_idx], keep_idx)."""
-        self._phase(_lib.PH_CORR)
         rows = self.N + self.n
-        self._read_flags(rows, False)
-        keep_idx = np.nonzero(self._keep[:rows])[0]
-        self._phase(_lib.PH_COMPACT)
+        if self.ahead:
+            k, _, st = self._wait_flags(1, rows, False)            # queued behind spatial_association; usually long done
+            keep_idx = np.nonzero(k)[0]
+            self.any_new = int(st.any_new)
+        else:
+            self._phase(_lib.PH_CORR)
+            self._read_flags(rows, False)
+            keep_idx = np.nonzero(self._keep[:rows])[0]
+            self.any_new = int(self.engine._state.any_new)
+            self._phase(_lib.PH_COMPACT)
         self.map_extras = {k: _index_values(v, keep_idx) for k, v in self.cat_extras.items()}
         self.cat_extras = {}
         self.N = int(len(keep_idx))
@@ -560,7 +627,9 @@ class Session:
         if (all_pred_box is not self.map_c or self.stage != Session.CORR or bm._session is not self or self.map_extras
                 or not self.check_valid or int(gap) != self.gap or int(count) != self.frame_id):
             return None
-        self._phase(_lib.PH_VALID)
+        if not self.ahead:
+            self._phase(_lib.PH_VALID)
+        self.valid_called = True
         self.N = None                                             # known on the device only
         self.map_c = self.new_container("map", None, all_pred_box.image_size)
         return self.map_c
@@ -573,7 +642,12 @@ class Session:
         if (float(fuser.H) != float(H) or float(fuser.W) != float(W)
                 or not np.array_equal(np.asarray(fuser.K, dtype=np.float32)[:3, :3], np.asarray(K, dtype=np.float32)[:3, :3])):
             return None
-        self._phase(_lib.PH_FUSE | _lib.PH_FINISH)
+        if self.ahead and self.check_valid and self.any_new and not self.valid_called:
+            return None                                            # the engine dropped stale rows the caller never asked to drop
+        if self.ahead:
+            self.ahead = False                                     # the engine did all of this behind spatial_association
+        else:
+            self._phase(_lib.PH_FUSE | _lib.PH_FINISH)
         e = self.engine
         e.M += self.n
         e._n_ub = (self.N if self.N is not None else e._n_ub)

@@ -316,6 +316,16 @@ int bf_engine_read_flags(bf_engine* e, int32_t* keep /*host*/, int32_t* success 
 /* Diagnostic read-back (synchronises) of engine-owned per-keyframe results: which = 0 refine iterations per box,
  * 1 CSR view offsets of the refined boxes, 2 map rows selected for refinement, 3 their `updated` flags. */
 int bf_engine_read_i32(bf_engine* e, int which, int32_t* out /*host*/, int count, void* stream);
+/* Run-ahead for the reference-shaped API (bits 1..6 of a keyframe whose bit 0 was issued): the NMS phase, an asynchronous copy
+ * of the keep / success flags of the first `rows` map rows + the state words to pinned memory (slot 0), a rollback snapshot, the
+ * correspondence phase, a copy of the keep flags + state (slot 1), then the rest of the keyframe - all queued at once, so the
+ * GPU works through the keyframe while the host is inside the caller's code between spatial_association and boxfusion.
+ * bf_engine_wait_flags waits for a slot's copy and returns HOST pointers into the engine's pinned buffers (valid until the
+ * next run-ahead).  bf_engine_rollback restores the state of right after the NMS phase (the caller strayed from demo.py's
+ * sequence): bits 2..6 can then be issued again one by one. */
+int bf_engine_run_ahead(bf_engine* e, int rows, void* stream);
+int bf_engine_wait_flags(bf_engine* e, int slot, int32_t** keep /*host*/, int32_t** success /*host*/, bf_engine_state** state /*host*/);
+int bf_engine_rollback(bf_engine* e, void* stream);
 /* Device pointers of engine-owned per-keyframe results (valid for the engine's lifetime). */
 int bf_engine_pointers(bf_engine* e, int32_t** keep, int32_t** success, bf_engine_state** state_dev, int32_t** refine_iters,
                        int32_t** todo);

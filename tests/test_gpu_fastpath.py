@@ -141,3 +141,73 @@ def test_fast_path_other_threshold_falls_back():
         ins_a, _ = a.make_pred_instances(kf)
         a.step(kf, ins_a, pose_np); b.step(kf, ins_b, pose_np)
         _same(a.snapshot(), b.snapshot(), k)
+
+
+def test_run_ahead_is_invisible():
+    """spatial_association queues the rest of the keyframe behind itself (fastpath.RUN_AHEAD).  A caller that looks at the
+    state between its calls, or stops following demo.py half-way through a keyframe, must see exactly what it would have seen
+    without it: the engine is rolled back to where the caller is."""
+    cfg = make_cfg("ca1m", pst_path=make_pst(256, seed=5), pst_size=256)
+    port.IOU_BACKEND = "c"
+    scene = SyntheticScene(n_objects=70, seed=14, max_det=28, shape="ca1m", tilt_noise=0.01)
+    a, b = FusionSession(api, cfg, device="cuda"), FusionSession(port, cfg)
+    looked = 0
+
+    def step_with_peeks(sess, kf, peek):
+        """driver._step with observations between the calls (what demo.py:294 does with its print of fusion_list)."""
+        impl, bm = sess.impl, sess.box_manager
+        ins, pose_np = sess.make_pred_instances(kf)
+        count = sess.count
+        sess.box_fuser.update_intrinsics(kf.image_size, kf.K)
+        sess.all_kf_pose[count] = kf.pose
+        sess.box_count += len(ins)
+        bm.init_new_predictions(len(ins), len(sess.per_frame_ins))
+        nb = len(sess.all_pred_box)
+        cur_global = sess.all_pred_box
+        allp = impl.Instances3D.cat([sess.all_pred_box, ins])
+        sess.per_frame_ins = impl.Instances3D.cat([sess.per_frame_ins, ins])
+        all_poses = np.concatenate((sess.all_poses, pose_np), axis=0)
+        mask, succ = impl.Instances3D.spatial_association(allp, cfg["box_fusion"]["nms_threshold"], bm, sess.per_frame_ins.cam_pose)
+        seen = {}
+        if peek == "after_nms":                              # lists and valid_num right after nms_3d
+            seen["fl"] = [list(l) for l in bm.fusion_list]
+            seen["valid"] = allp.valid_num.cpu().numpy().copy()
+        ck = [i - nb for i in mask if i >= nb]
+        cs = [i - nb for i in succ if i >= nb]
+        keep_idx = np.asarray(mask)
+        if len(ck) > 0:
+            allp, all_poses, keep_idx = impl.Instances3D.correspondence_association(
+                cfg, bm, ck, cs, ins, cur_global, allp, all_poses, sess.per_frame_ins.cam_pose, count, mask, torch.from_numpy(kf.K),
+                sess.all_kf_pose, threshold=cfg["association"]["small_threshold"], H=kf.image_size[1], W=kf.image_size[0])
+            bm.update(keep_idx)
+            if peek == "after_update":                       # demo.py:294; and the map before it is fused
+                seen["fl"] = [list(l) for l in bm.fusion_list]
+                seen["tensor"] = allp.pred_boxes_3d.tensor.cpu().numpy().copy()
+                seen["flag"] = list(bm.fusion_flag)
+            if peek != "skip_fusion":
+                sess.box_fuser.boxfusion(allp, sess.per_frame_ins, bm)
+        else:
+            allp = allp[mask]
+            all_poses = all_poses[mask]
+            bm.update(keep_idx)
+        sess.all_pred_box, sess.all_poses = allp, all_poses
+        sess.count += 1
+        return seen
+
+    for k in range(22):
+        kf = scene.keyframe(k)
+        peek = {6: "after_nms", 9: "after_update", 12: "skip_fusion", 15: "after_update", 16: "after_nms"}.get(k)
+        if k < 2 or peek is None:
+            a.step(kf); b.step(kf)
+        else:
+            fast_before = a.box_manager._session is not None
+            sa, sb = step_with_peeks(a, kf, peek), step_with_peeks(b, kf, peek)
+            looked += int(fast_before)
+            assert sa.keys() == sb.keys()
+            for key in sa:
+                if key in ("fl", "flag"):
+                    assert sa[key] == [[int(x) for x in l] for l in sb[key]] if key == "fl" else sa[key] == [int(x) for x in sb[key]], (k, key)
+                else:
+                    assert np.array_equal(_bits(sa[key]), _bits(np.asarray(sb[key]))), (k, key)
+        _same(a.snapshot(), b.snapshot(), k)
+    assert looked >= 4 and a.box_manager._session is not None
