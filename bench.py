@@ -274,6 +274,15 @@ def run_ours(args, rank, world, local_rank):
     barrier(); wall_e2e = time.perf_counter() - t0
     n_timed = len(step_ms_e2e)
     h2d_b, d2h_b = ops.Profile.h2d_bytes, ops.Profile.d2h_bytes
+    # ---- context: the same pass with every call on its own (round 1's implementation; the engine-backed path switched off) ----
+    from boxfusion_b200 import fastpath
+    fastpath.ENABLED = False
+    try:
+        step_ms_cbc, sess3 = run_api(seqs, False)
+    finally:
+        fastpath.ENABLED = True
+    cbc_h2d, cbc_d2h = ops.Profile.h2d_bytes, ops.Profile.d2h_bytes
+    assert len(sess3.all_pred_box) == len(sess2.all_pred_box)
     # ---- pass 3: the engine's own entry, host inputs, same keyframes -----------------
     barrier(); t0 = time.perf_counter()
     step_ms_eng, eng, _ = run_engine(seqs)
@@ -340,6 +349,10 @@ def run_ours(args, rank, world, local_rank):
                        "note": "same keyframes through bf_engine_step (one C call = one H2D copy + one CUDA-graph launch per keyframe; "
                                "host packing of the detections incl. both pose inverses is inside the timed region); final map "
                                "identical to the reference-shaped API's"},
+        "e2e_call_by_call": {"ms_per_step": round(sum(step_ms_cbc) / len(step_ms_cbc), 4), "h2d_bytes_per_step": int(cbc_h2d / max(n_all, 1)),
+                             "d2h_bytes_per_step": int(cbc_d2h / max(n_all, 1)), "rank": 0,
+                             "note": "context: the same keyframes with boxfusion_b200.fastpath.ENABLED = False - every reference-shaped call uploads, "
+                                     "launches and downloads on its own (round 1's implementation of the API)"},
         "gpu_launches": int(launches), "calls": call_counts, "l2": "flushed between steps (256 MiB memset outside the step events)",
         "final_map_boxes": len(sess.all_pred_box), "keyframes_run": n_all,
         "wall_s": {"resident": round(wall_resident, 3), "e2e": round(wall_e2e, 3), "engine": round(wall_eng, 3)},

@@ -1,9 +1,11 @@
 // K1 - batched oriented-3D IoU and its use by the NMS entry.
 //
 // Pipeline (all on one stream, no host round trip):
-//   bf_planes_kernel     per box: 12 float64 hull planes + float32 AABB            (N threads)
-//   bf_pairs_kernel      per pair: exact AABB reject -> analytic IoU (ANALYTIC mode, co-axial pairs)
-//                        or append to a candidate list                             (M*N threads)
+//   bf_planes_kernel     per box: 12 float64 hull planes + float32 AABB as two float4 (6 threads per box)
+//   bf_pairs_kernel      tiles of 8 x 128 pairs: the A boxes' AABBs staged in shared memory, every thread keeps its B box's
+//                        AABB in registers (two coalesced float4 loads); exact AABB reject -> analytic IoU (ANALYTIC mode,
+//                        co-axial pairs; corners read as float4, Sutherland-Hodgman clip in registers) or append to a
+//                        candidate list
 //   bf_count_kernel      per candidate, one CTA: containment gate (40 points over the threads), then the
 //                        25^3 inside-counts by per-row bisection (625 rows over the threads), IoU in
 //                        float64; writes the dense matrix and/or NMS mask bits       (persistent grid)
@@ -34,7 +36,8 @@ __global__ void bf_planes_kernel(const float* __restrict__ corners, const bf_dim
 #pragma unroll
             for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], c[3 * i + k]); hi[k] = fmaxf(hi[k], c[3 * i + k]); }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { aabb[6 * n + k] = lo[k]; aabb[6 * n + 3 + k] = hi[k]; }
+        for (int k = 0; k < 3; ++k) { aabb[8 * n + k] = lo[k]; aabb[8 * n + 4 + k] = hi[k]; }
+        aabb[8 * n + 3] = 0.f; aabb[8 * n + 7] = 0.f;         // two float4 per box: (lo.xyz, 0), (hi.xyz, 0)
     }
     }
 }
@@ -43,81 +46,129 @@ __global__ void bf_planes_kernel(const float* __restrict__ corners, const bf_dim
 // Analytic IoU of two boxes that share an axis (gravity-aligned boxes): BEV Sutherland-Hodgman clip of
 // B's footprint against A's rectangle x overlap along the shared axis, float64.  Returns false when
 // no pair of box axes is parallel within 1-1e-6 (caller falls back to the sampled estimator).
+// Round 2: the 24 corner floats of each box arrive as six float4 loads, and the clip polygon (at most 8 vertices) lives in
+// registers - every loop below is fully unrolled over static indices, the append position is a predicate, not an address.
+// Work on the straight-line path (published as SURVEY section 8(d) asks): frames 2 x 66, axis search <= 9 x 5, footprint 44,
+// clip 4 edges x 8 slots x (compare + interpolate 10) = 320, shoelace 8 x 4, volumes and ratio 14: ~600 flop per co-axial pair
+// (float64), 48 B per box in, 8 B out.
 struct bf_frame { double c[3]; double ax[3][3]; double half[3]; };
 
-__device__ inline void bf_frame_from_corners(const float* __restrict__ c24, bf_frame& F) {
+__device__ __forceinline__ void bf_load_corners(const float* __restrict__ corners, int n, float (&c)[24]) {
+    const float4* q = reinterpret_cast<const float4*>(corners + 24 * (size_t)n);     // 96 B per box: 16-byte aligned rows
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const float4 v = __ldg(q + k); c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w; }
+}
+
+__device__ __forceinline__ void bf_frame_from_corners(const float (&c24)[24], bf_frame& F) {
     // v1-v0 = l along X, v3-v0 = h along Y, v4-v0 = w along Z (boxes.py:756-766)
-    const int other[3] = {1, 3, 4};
+#pragma unroll
     for (int k = 0; k < 3; ++k) F.c[k] = 0.5 * ((double)c24[k] + (double)c24[18 + k]);     // (v0+v6)/2
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
+        const int other = (a == 0) ? 1 : (a == 1 ? 3 : 4);
         double e[3], n2 = 0;
-        for (int k = 0; k < 3; ++k) { e[k] = (double)c24[3 * other[a] + k] - (double)c24[k]; n2 += e[k] * e[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { e[k] = (double)c24[3 * other + k] - (double)c24[k]; n2 += e[k] * e[k]; }
         const double len = sqrt(n2);
         F.half[a] = 0.5 * len;
+#pragma unroll
         for (int k = 0; k < 3; ++k) F.ax[a][k] = len > 0 ? e[k] / len : 0.0;
     }
 }
 
-__device__ inline bool bf_analytic_iou(const float* __restrict__ ca, const float* __restrict__ cb, double* iou_out) {
+// row a of a 3x3 / 3-vector held in registers, selected without an address (a is data-dependent)
+__device__ __forceinline__ double bf_sel3(const double (&v)[3], int a) { return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]); }
+__device__ __forceinline__ void bf_row3(const double (&m)[3][3], int a, double (&r)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[k] = a == 0 ? m[0][k] : (a == 1 ? m[1][k] : m[2][k]);
+}
+
+__device__ __forceinline__ bool bf_analytic_iou(const float (&ca)[24], const float (&cb)[24], double* iou_out) {
     bf_frame A, B;
     bf_frame_from_corners(ca, A);
     bf_frame_from_corners(cb, B);
     int ia = -1, ib = -1;
     // prefer the gravity axis (local Y, index 1) of both boxes
-    const int pref[3] = {1, 0, 2};
-    for (int i = 0; i < 3 && ia < 0; ++i)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const int a = pref[i], b = pref[j];
+            const int a = (i == 0) ? 1 : (i == 1 ? 0 : 2), b = (j == 0) ? 1 : (j == 1 ? 0 : 2);
             const double d = A.ax[a][0] * B.ax[b][0] + A.ax[a][1] * B.ax[b][1] + A.ax[a][2] * B.ax[b][2];
-            if (fabs(d) >= 1.0 - 1e-6) { ia = a; ib = b; break; }
+            if (ia < 0 && fabs(d) >= 1.0 - 1e-6) { ia = a; ib = b; }
         }
     if (ia < 0) return false;
-    const double* u = A.ax[ia];
+    double u[3], P[3], Q[3], Bm[3], Bn[3];
     const int pa = (ia + 1) % 3, qa = (ia + 2) % 3;       // A's in-plane axes
     const int mb = (ib + 1) % 3, nb = (ib + 2) % 3;       // B's in-plane axes
+    bf_row3(A.ax, ia, u); bf_row3(A.ax, pa, P); bf_row3(A.ax, qa, Q); bf_row3(B.ax, mb, Bm); bf_row3(B.ax, nb, Bn);
+    const double hA = bf_sel3(A.half, ia), hB = bf_sel3(B.half, ib);
     // height overlap along u
-    double dc[3] = {B.c[0] - A.c[0], B.c[1] - A.c[1], B.c[2] - A.c[2]};
+    const double dc[3] = {B.c[0] - A.c[0], B.c[1] - A.c[1], B.c[2] - A.c[2]};
     const double hb = dc[0] * u[0] + dc[1] * u[1] + dc[2] * u[2];
-    const double top = fmin(A.half[ia], hb + B.half[ib]), bot = fmax(-A.half[ia], hb - B.half[ib]);
+    const double top = fmin(hA, hb + hB), bot = fmax(-hA, hb - hB);
     const double oh = top - bot;
     const double volA = 8.0 * A.half[0] * A.half[1] * A.half[2], volB = 8.0 * B.half[0] * B.half[1] * B.half[2];
     if (oh <= 0) { *iou_out = 0.0; return true; }
     // B footprint in A's (p,q) coordinates
-    const double* P = A.ax[pa]; const double* Q = A.ax[qa];
     const double cp = dc[0] * P[0] + dc[1] * P[1] + dc[2] * P[2], cq = dc[0] * Q[0] + dc[1] * Q[1] + dc[2] * Q[2];
-    const double mp = (B.ax[mb][0] * P[0] + B.ax[mb][1] * P[1] + B.ax[mb][2] * P[2]) * B.half[mb];
-    const double mq = (B.ax[mb][0] * Q[0] + B.ax[mb][1] * Q[1] + B.ax[mb][2] * Q[2]) * B.half[mb];
-    const double np_ = (B.ax[nb][0] * P[0] + B.ax[nb][1] * P[1] + B.ax[nb][2] * P[2]) * B.half[nb];
-    const double nq = (B.ax[nb][0] * Q[0] + B.ax[nb][1] * Q[1] + B.ax[nb][2] * Q[2]) * B.half[nb];
-    double px[10], py[10], qx[10], qy[10];
+    const double hm = bf_sel3(B.half, mb), hn = bf_sel3(B.half, nb);
+    const double mp = (Bm[0] * P[0] + Bm[1] * P[1] + Bm[2] * P[2]) * hm;
+    const double mq = (Bm[0] * Q[0] + Bm[1] * Q[1] + Bm[2] * Q[2]) * hm;
+    const double np_ = (Bn[0] * P[0] + Bn[1] * P[1] + Bn[2] * P[2]) * hn;
+    const double nq = (Bn[0] * Q[0] + Bn[1] * Q[1] + Bn[2] * Q[2]) * hn;
+    double px[8], py[8];
     px[0] = cp - mp - np_; py[0] = cq - mq - nq;
     px[1] = cp + mp - np_; py[1] = cq + mq - nq;
     px[2] = cp + mp + np_; py[2] = cq + mq + nq;
     px[3] = cp - mp + np_; py[3] = cq - mq + nq;
+#pragma unroll
+    for (int k = 4; k < 8; ++k) { px[k] = 0.0; py[k] = 0.0; }
     int n = 4;
-    const double ha = A.half[pa], hq = A.half[qa];
-    // Sutherland-Hodgman against x<=ha, x>=-ha, y<=hq, y>=-hq
-    for (int e = 0; e < 4 && n > 0; ++e) {
+    const double ha = bf_sel3(A.half, pa), hq = bf_sel3(A.half, qa);
+    // Sutherland-Hodgman against x<=ha, x>=-ha, y<=hq, y>=-hq; a rectangle clipped by four half-planes has <= 8 vertices
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
         const double lim = (e < 2) ? ha : hq;
         const double sgn = (e & 1) ? -1.0 : 1.0;          // inside: sgn*coord <= lim
+        double qx[8], qy[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { qx[k] = 0.0; qy[k] = 0.0; }
         int m = 0;
-        for (int i = 0; i < n; ++i) {
-            const int j = (i + 1 == n) ? 0 : i + 1;
-            const double ci = sgn * ((e < 2) ? px[i] : py[i]), cj = sgn * ((e < 2) ? px[j] : py[j]);
-            const bool ini = ci <= lim, inj = cj <= lim;
-            if (ini) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
-            if (ini != inj) {
-                const double t = (lim - ci) / (cj - ci);
-                qx[m] = px[i] + t * (px[j] - px[i]);
-                qy[m] = py[i] + t * (py[j] - py[i]);
-                ++m;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < n) {
+                // successor of vertex i (vertex 0 after the last one): static index, dynamic wrap
+                double jx = px[0], jy = py[0];
+                if (i + 1 < n) { jx = px[(i + 1) & 7]; jy = py[(i + 1) & 7]; }
+                const double ci = sgn * ((e < 2) ? px[i] : py[i]), cj = sgn * ((e < 2) ? jx : jy);
+                const bool ini = ci <= lim, inj = cj <= lim;
+                if (ini) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (k == m) { qx[k] = px[i]; qy[k] = py[i]; }
+                    ++m;
+                }
+                if (ini != inj) {
+                    const double t = (lim - ci) / (cj - ci);
+                    const double nx = px[i] + t * (jx - px[i]), ny = py[i] + t * (jy - py[i]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (k == m) { qx[k] = nx; qy[k] = ny; }
+                    ++m;
+                }
             }
         }
-        n = m;
-        for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
+        n = m < 8 ? m : 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { px[k] = qx[k]; py[k] = qy[k]; }
     }
     double area = 0;
-    for (int i = 0; i < n; ++i) { const int j = (i + 1 == n) ? 0 : i + 1; area += px[i] * py[j] - px[j] * py[i]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < n) {
+            double jx = px[0], jy = py[0];
+            if (i + 1 < n) { jx = px[(i + 1) & 7]; jy = py[(i + 1) & 7]; }
+            area += px[i] * jy - jx * py[i];
+        }
     area = 0.5 * fabs(area);
     const double vi = area * oh;
     *iou_out = vi / (volA + volB - vi);
@@ -125,11 +176,17 @@ __device__ inline bool bf_analytic_iou(const float* __restrict__ ca, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// One thread per pair (grid-stride).  triangle != 0: A and B are the same set and only a < b is evaluated (NMS).
-// Outputs: dense iou/counts zero-filled (when given), work list of gate-passing pairs, stats.
+// Tiles of BF_TILE_A x 128 pairs (grid-stride over the tiles).  triangle != 0: A is rows [a_off, a_off + M) of B and only
+// pairs with a_off + a < b are evaluated (NMS).  Outputs: dense iou/counts zero-filled (when given), work list of gate-passing
+// pairs, stats.
 // counters: [0] work items, [1] pairs, [2] AABB-passing, [3] gate-passing, [4] analytic, [5] overflow, [6] NMS edges
 // M / N are host values or read from device memory (bf_dimref); the mask row stride is W = ceil(N/32) of the actual N.
-__global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA,
+// Data movement: the A boxes' AABBs of a tile are staged in shared memory as float4 (SoA: lo, hi), every thread keeps the AABB
+// of its B box in registers (two float4 loads, 32 contiguous bytes per thread: coalesced), the zero fill of the dense outputs
+// is coalesced over b for a fixed a.
+#define BF_TILE_A 8
+__global__ void __launch_bounds__(128)
+bf_pairs_kernel(const float* __restrict__ cornersA, const float* __restrict__ aabbA,
                                 const double* __restrict__ planesA, const bf_dimref Md, const float* __restrict__ cornersB,
                                 const float* __restrict__ aabbB, const double* __restrict__ planesB, const bf_dimref Nd,
                                 int triangle, int a_off, int mode, double* __restrict__ iou, int32_t* __restrict__ counts,
@@ -137,48 +194,81 @@ __global__ void bf_pairs_kernel(const float* __restrict__ cornersA, const float*
                                 // NMS outputs (ANALYTIC hits are thresholded here)
                                 double thr, const int32_t* __restrict__ rank, uint32_t* __restrict__ mask,
                                 uint32_t* __restrict__ rowany, unsigned long long* __restrict__ edges, int edge_cap) {
+    __shared__ float4 s_lo[BF_TILE_A], s_hi[BF_TILE_A];
     const int M = bf_dim(Md), N = bf_dim(Nd);
-    const int W = (N + 31) >> 5;
     const long long total = (long long)M * N;
-    const long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // triangle: A is rows [a_off, a_off + M) of B and only pairs with a_off + a < b are evaluated
-    if (p0 == 0) counters[1] = triangle ? (unsigned long long)M * (unsigned long long)(2LL * (N - a_off) - M - 1 > 0 ? 2LL * (N - a_off) - M - 1 : 0) / 2ULL : (unsigned long long)total;
-    for (long long p = p0; p < total; p += (long long)gridDim.x * blockDim.x) {
-        const int a = (int)(p / N), b = (int)(p % N);
-        if (iou) iou[p] = 0.0;
-        if (counts) { counts[3 * p] = 0; counts[3 * p + 1] = 0; counts[3 * p + 2] = 0; }
-        if (triangle && a + a_off >= b) continue;
-        // exact reject: a point within 1e-6 of every face plane of a box lies within its AABB grown by 1e-4
-        const float* ba = aabbA + 6 * a;
-        const float* bb = aabbB + 6 * b;
-        const float m = 1e-4f;
-        if (ba[0] > bb[3] + m || bb[0] > ba[3] + m || ba[1] > bb[4] + m || bb[1] > ba[4] + m || ba[2] > bb[5] + m ||
-            bb[2] > ba[5] + m)
-            continue;
-        atomicAdd(&counters[2], 1ULL);
-        const float* ca = cornersA + 24 * a;
-        const float* cb = cornersB + 24 * b;
-        if (mode == BF_IOU_ANALYTIC) {
-            double v;
-            if (bf_analytic_iou(ca, cb, &v)) {
-                atomicAdd(&counters[4], 1ULL);
-                if (iou) iou[p] = v;
-                if (rank && v > thr) {
-                    const int ra = rank[a + a_off], rb = rank[b];
-                    const int r0 = min(ra, rb), r1 = max(ra, rb);
-                    if (mask) {
-                        atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
-                        atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
-                    }
-                    const unsigned long long e = atomicAdd(&counters[6], 1ULL);
-                    if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
-                }
-                continue;
-            }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        counters[1] = triangle ? (unsigned long long)M * (unsigned long long)(2LL * (N - a_off) - M - 1 > 0 ? 2LL * (N - a_off) - M - 1 : 0) / 2ULL : (unsigned long long)total;
+    const int tiles_a = (M + BF_TILE_A - 1) / BF_TILE_A, tiles_b = (N + 127) / 128;
+    const float4* bb4 = reinterpret_cast<const float4*>(aabbB);
+    const float4* ba4 = reinterpret_cast<const float4*>(aabbA);
+    const float m = 1e-4f;
+    unsigned local_aabb = 0;
+    for (long long tile = blockIdx.x; tile < (long long)tiles_a * tiles_b; tile += gridDim.x) {
+        const int ta = (int)(tile / tiles_b), tb = (int)(tile - (long long)ta * tiles_b);
+        const int a0 = ta * BF_TILE_A, b = tb * 128 + threadIdx.x;
+        if (triangle && a0 + a_off >= tb * 128 + 127) {               // the whole tile lies on or below the diagonal
+            if (!iou && !counts) continue;
         }
-        const unsigned long long slot = atomicAdd(&counters[0], 1ULL);      // candidate: gate + counts in bf_count_kernel
-        if (slot < (unsigned long long)work_cap) { work[slot].a = a; work[slot].b = b; }
-        else atomicExch(&counters[5], 1ULL);
+        __syncthreads();
+        if (threadIdx.x < BF_TILE_A && a0 + threadIdx.x < M) { s_lo[threadIdx.x] = __ldg(ba4 + 2 * (a0 + threadIdx.x)); s_hi[threadIdx.x] = __ldg(ba4 + 2 * (a0 + threadIdx.x) + 1); }
+        __syncthreads();
+        if (b >= N) continue;
+        const float4 blo = __ldg(bb4 + 2 * b), bhi = __ldg(bb4 + 2 * b + 1);
+#pragma unroll
+        for (int k = 0; k < BF_TILE_A; ++k) {
+            const int a = a0 + k;
+            if (a >= M) break;
+            const long long p = (long long)a * N + b;
+            if (iou) iou[p] = 0.0;
+            if (counts) { counts[3 * p] = 0; counts[3 * p + 1] = 0; counts[3 * p + 2] = 0; }
+            if (triangle && a + a_off >= b) continue;
+            // exact reject: a point within 1e-6 of every face plane of a box lies within its AABB grown by 1e-4
+            const float4 alo = s_lo[k], ahi = s_hi[k];
+            if (alo.x > bhi.x + m || blo.x > ahi.x + m || alo.y > bhi.y + m || blo.y > ahi.y + m || alo.z > bhi.z + m ||
+                blo.z > ahi.z + m)
+                continue;
+            ++local_aabb;
+            const unsigned long long slot = atomicAdd(&counters[0], 1ULL);      // candidate: gate + counts in bf_count_kernel
+            if (slot < (unsigned long long)work_cap) { work[slot].a = a; work[slot].b = b; }
+            else atomicExch(&counters[5], 1ULL);
+        }
+    }
+    if (local_aabb) atomicAdd(&counters[2], (unsigned long long)local_aabb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ANALYTIC mode: one thread per AABB-passing candidate (grid-stride over the work list).  Co-axial pairs get their IoU here
+// and leave the list (a = -1); the others stay for the sampled estimator below.
+__global__ void __launch_bounds__(64)
+bf_analytic_kernel(const float* __restrict__ cornersA, const float* __restrict__ cornersB, const bf_dimref Nd, int a_off,
+                   bf_work_item* __restrict__ work, int work_cap, unsigned long long* __restrict__ counters,
+                   double* __restrict__ iou, double thr, const int32_t* __restrict__ rank, uint32_t* __restrict__ mask,
+                   uint32_t* __restrict__ rowany, unsigned long long* __restrict__ edges, int edge_cap) {
+    const int N = bf_dim(Nd);
+    const int W = (N + 31) >> 5;
+    unsigned long long nwork = counters[0];
+    if (nwork > (unsigned long long)work_cap) nwork = work_cap;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += (unsigned long long)gridDim.x * blockDim.x) {
+        const int a = work[w].a, b = work[w].b;
+        float ca[24], cb[24];
+        bf_load_corners(cornersA, a, ca);
+        bf_load_corners(cornersB, b, cb);
+        double v;
+        if (!bf_analytic_iou(ca, cb, &v)) continue;
+        work[w].a = -1;                                                   // done: bf_count_kernel skips it
+        atomicAdd(&counters[4], 1ULL);
+        if (iou) iou[(size_t)a * N + b] = v;
+        if (rank && v > thr) {
+            const int ra = rank[a + a_off], rb = rank[b];
+            const int r0 = min(ra, rb), r1 = max(ra, rb);
+            if (mask) {
+                atomicOr(&mask[(size_t)r0 * W + (r1 >> 5)], 1u << (r1 & 31));
+                atomicOr(&rowany[r0 >> 5], 1u << (r0 & 31));
+            }
+            const unsigned long long e = atomicAdd(&counters[6], 1ULL);
+            if (e < (unsigned long long)edge_cap) edges[e] = ((unsigned long long)r0 << 32) | (unsigned long long)r1;
+        }
     }
 }
 
@@ -203,12 +293,13 @@ bf_count_kernel(const float* __restrict__ cornersA, const float* __restrict__ aa
     if (nwork > (unsigned long long)work_cap) nwork = work_cap;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int a = work[w].a, b = work[w].b;
+        if (a < 0) continue;                                              // ANALYTIC mode settled this pair (block-uniform)
         __syncthreads();
         if (tid < 48) { s_pl[0][tid] = planesA[48 * (size_t)a + tid]; s_pl[1][tid] = planesB[48 * (size_t)b + tid]; }
         if (tid >= 64 && tid < 88) { s_c[0][tid - 64] = cornersA[24 * (size_t)a + tid - 64]; s_c[1][tid - 64] = cornersB[24 * (size_t)b + tid - 64]; }
         if (tid >= 96 && tid < 96 + 3 * BF_NS) {
             const int ax = (tid - 96) / BF_NS, i = (tid - 96) - ax * BF_NS;
-            const float lo = fminf(aabbA[6 * a + ax], aabbB[6 * b + ax]), hi = fmaxf(aabbA[6 * a + 3 + ax], aabbB[6 * b + 3 + ax]);   // instances.py:581-582
+            const float lo = fminf(aabbA[8 * a + ax], aabbB[8 * b + ax]), hi = fmaxf(aabbA[8 * a + 4 + ax], aabbB[8 * b + 4 + ax]);   // instances.py:581-582
             s_grid[ax][i] = (double)bf_linspace25(lo, hi, i);
         }
         __syncthreads();
@@ -283,7 +374,7 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float*
     const bool dev_sized = Md.dev || Nd.dev;
     const int stride_grid = h->sm_count * 8;
     if ((rc = bf_scratch(h, BF_SCRATCH_PLANES_A, sizeof(double) * 48 * (size_t)M, &p))) return rc; plA = (double*)p;
-    if ((rc = bf_scratch(h, BF_SCRATCH_AABB_A, sizeof(float) * 6 * (size_t)M, &p))) return rc; bbA = (float*)p;
+    if ((rc = bf_scratch(h, BF_SCRATCH_AABB_A, sizeof(float) * 8 * (size_t)M, &p))) return rc; bbA = (float*)p;
     {
         const int g = bf_blocks(6LL * M, 96);
         bf_planes_kernel<<<(dev_sized && g > stride_grid) ? stride_grid : g, 96, 0, st>>>(cornersA, Md, plA, bbA);
@@ -292,7 +383,7 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float*
     if (cornersB == cornersA && Nd.host == Md.host && Nd.dev == Md.dev) { plB = plA; bbB = bbA; }
     else {
         if ((rc = bf_scratch(h, BF_SCRATCH_PLANES_B, sizeof(double) * 48 * (size_t)N, &p))) return rc; plB = (double*)p;
-        if ((rc = bf_scratch(h, BF_SCRATCH_AABB_B, sizeof(float) * 6 * (size_t)N, &p))) return rc; bbB = (float*)p;
+        if ((rc = bf_scratch(h, BF_SCRATCH_AABB_B, sizeof(float) * 8 * (size_t)N, &p))) return rc; bbB = (float*)p;
         const int g = bf_blocks(6LL * N, 96);
         bf_planes_kernel<<<(dev_sized && g > stride_grid) ? stride_grid : g, 96, 0, st>>>(cornersB, Nd, plB, bbB);
         BF_LAUNCH_CHECK(h, "bf_planes_kernel");
@@ -308,8 +399,9 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float*
     unsigned long long* counters = (unsigned long long*)p;
     BF_CUDA(h, cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 8, st));
     {
-        // fixed, machine-filling grid when the sizes live on the device; exact grid otherwise (capped: the kernel strides)
-        long long g = (total + 127) / 128;
+        // one CTA per tile of 8 x 128 pairs; fixed, machine-filling grid when the sizes live on the device, capped otherwise
+        // (the kernel strides over the tiles)
+        long long g = (long long)((M + BF_TILE_A - 1) / BF_TILE_A) * ((N + 127) / 128);
         const long long gcap = (long long)h->sm_count * (dev_sized ? 16 : 64);
         if (g > gcap) g = gcap;
         if (g < 1) g = 1;
@@ -317,6 +409,11 @@ int bf_iou3d_run(bf_handle* h, const float* cornersA, bf_dimref Md, const float*
                                                      iou, counts, work, (int)cap, counters, thr, rank, mask, rowany, edges, edge_cap);
     }
     BF_LAUNCH_CHECK(h, "bf_pairs_kernel");
+    if (mode == BF_IOU_ANALYTIC) {
+        bf_analytic_kernel<<<h->sm_count * 2, 64, 0, st>>>(cornersA, cornersB, Nd, a_off, work, (int)cap, counters, iou, thr, rank, mask,
+                                                           rowany, edges, edge_cap);
+        BF_LAUNCH_CHECK(h, "bf_analytic_kernel");
+    }
     const int grid = h->sm_count * 3;
     bf_count_kernel<<<grid, BF_COUNT_THREADS, 0, st>>>(cornersA, bbA, plA, cornersB, bbB, plB, Nd, a_off, work, (int)cap, counters,
                                                        iou, counts, thr, rank, mask, rowany, edges, edge_cap);
