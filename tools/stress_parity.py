@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--with-port", type=int, default=4, help="first K seeds are also checked against the CPU port")
     args = ap.parse_args()
     port.IOU_BACKEND = "c_batch"
-    stats = {"keyframes": 0, "corr_events": 0, "swaps_or_merges": 0, "fused": 0, "mismatch": 0}
+    stats = {"keyframes": 0, "keyframes_on_engine_backed_api": 0, "swaps_or_merges": 0, "fused": 0, "mismatch": 0}
     for seed in range(args.seeds):
         shape = "scannet" if seed % 2 else "ca1m"
         tilt = (0.0, 0.01, 0.03)[seed % 3]
@@ -47,6 +47,7 @@ def main():
             kf = scene.keyframe(k)
             eng.step(pack_keyframe(kf.tensor_cam, kf.R_cam, kf.scores, kf.pred_boxes, kf.pred_proj_xy, kf.pose),
                      kf.tensor_cam.shape[0], kf.K, kf.image_size)
+            stats["keyframes_on_engine_backed_api"] += int(sess.box_manager._session is not None)
             sess.step(kf)
             a, b = eng.snapshot(), sess.snapshot()
             c = None
