@@ -20,6 +20,7 @@ SOURCES = {
     "bf_assoc.cu": [],
     "bf_engine.cu": [],
     "bf_refine.cu": ["-fmad=false"],
+    "bf_debug.cu": ["-fmad=false"],
 }
 
 

@@ -51,7 +51,8 @@ float bfh_iou_points(const float* a16, const float* b16, float img_w, float img_
     P2 h0[8];
     for (int k = 0; k < 8; ++k) h0[k] = hm[k];
     int fb = 0, over = 0;
-    const float iou = rolled ? bf_hull_iou<true>(h0, hm, n0, vw, &over, &fb) : bf_hull_iou<false>(h0, hm, n0, vw, &over, &fb);
+    bf_divrange dk = bf_divrange_init();
+    const float iou = rolled ? bf_hull_iou<true>(h0, hm, n0, vw, &over, &fb, dk) : bf_hull_iou<false>(h0, hm, n0, vw, &over, &fb, dk);
     if (fallbacks) *fallbacks = fb;
     if (overflow) *overflow = over;
     return iou;
