@@ -586,6 +586,17 @@ extern "C" int bf_refine(bf_handle* h, const float* pst, int P, const float* per
 
 extern "C" int bf_refine_last_launch(bf_handle* h) { return h ? h->last_refine_cluster : 0; }
 
+// Diagnostics: evaluations that were redone with plain divisions because an operand left the window of the branch-free ones
+// (bf_refine_eval.cuh, bf_fdiv) since the last reset.  Synchronises the device.
+extern "C" long long bf_debug_cold_redos(bf_handle* h, int reset) {
+    bf_device_guard guard(h);
+    if (!h) return -1;
+    unsigned int v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(&v, bf_cold_redos, sizeof(v)) != cudaSuccess) return -1;
+    if (reset) { const unsigned int z = 0; if (cudaMemcpyToSymbol(bf_cold_redos, &z, sizeof(z)) != cudaSuccess) return -1; }
+    return (long long)v;
+}
+
 // ---- evaluate_iou as a stand-alone entry (tests / diagnostics) -------------------------------------
 __global__ void __launch_bounds__(BF_REFINE_THREADS)
 bf_evaluate_kernel(const float* __restrict__ pst, int P, const float* __restrict__ box6, const float* __restrict__ rot9,

@@ -68,6 +68,7 @@ class FusionEngine:
         driven concurrently from one host thread (bench.py --workload c5); every engine has its own scratch in any case."""
         self.cfg = cfg
         self.dev = ops._dev(device if str(device) != "cuda" else None)
+        self._dev_index = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
         if map_capacity > 65536:
             raise ValueError("map_capacity is limited to 65536 rows")
         self.lib = _lib.load_library()
@@ -143,7 +144,7 @@ class FusionEngine:
         return {k: torch.zeros((self.ncap, w) if w > 1 else (self.ncap,), dtype=dt, device=d) for k, w, dt in _MAP_FIELDS}
 
     def _st(self) -> int:
-        return self._stream_ptr if self._stream_ptr is not None else torch.cuda.current_stream(self.dev).cuda_stream
+        return self._stream_ptr if self._stream_ptr is not None else _lib._raw_stream(self._dev_index)
 
     def _check(self, rc, what):
         if rc != 0:

@@ -202,6 +202,7 @@ class Session:
         self._state_ref = ctypes.byref(self.engine._state)
         self._stp = self.engine._st()   # stream of the keyframe in flight (looked up once per keyframe)
         self.image_size = None
+        self._flag_views = {}           # numpy / ctypes views of the engine's pinned flag buffers, per slot
 
     # ---- helpers ----------------------------------------------------------------------------------------------
     def _phase(self, phases):
@@ -242,12 +243,20 @@ class Session:
         rc = e.lib.bf_engine_wait_flags(e.e, slot, ctypes.byref(pk), ctypes.byref(ps), ctypes.byref(pst))
         if rc:
             e._check(rc, "bf_engine_wait_flags")
-        I32 = ctypes.POINTER(ctypes.c_int32)
-        keep = np.ctypeslib.as_array(ctypes.cast(pk, I32), shape=(rows,)) if rows else np.zeros(0, np.int32)
-        succ = np.ctypeslib.as_array(ctypes.cast(ps, I32), shape=(rows,)) if (rows and want_success) else None
-        st = ctypes.cast(pst, ctypes.POINTER(_lib.EngineState)).contents
+        key = (slot, pk.value, ps.value, pst.value)
+        views = self._flag_views.get(key)
+        if views is None:                                          # the pinned flag buffers of a slot never move: wrap them once
+            I32 = ctypes.POINTER(ctypes.c_int32)
+            cap = int(e.ncap)
+            views = (np.ctypeslib.as_array(ctypes.cast(pk, I32), shape=(cap,)), np.ctypeslib.as_array(ctypes.cast(ps, I32), shape=(cap,)),
+                     ctypes.cast(pst, ctypes.POINTER(_lib.EngineState)).contents)
+            self._flag_views[key] = views
+        keep = views[0][:rows]
+        succ = views[1][:rows] if want_success else None
+        st = views[2]
         ops.Profile.d2h_bytes += 4 * rows * (2 if want_success else 1) + ctypes.sizeof(_lib.EngineState)
-        if any(st.status[i] for i in range(8)):
+        s8 = st.status
+        if s8[0] | s8[1] | s8[2] | s8[3] | s8[4] | s8[5] | s8[6] | s8[7]:
             e.check_status()
         return keep, succ, st
 

@@ -334,6 +334,15 @@ def last_refine_launch(device=None) -> dict:
     return {"variant": ("latency", "mid", "saturated")[v // 1000000], "cluster": (v % 1000000) // 1000, "threads": v % 1000}
 
 
+def cold_redos(device=None, reset: bool = True) -> int:
+    """Diagnostic: evaluations redone with plain divisions since the last reset (bf_debug_cold_redos)."""
+    h = handle(device)
+    v = int(h.lib.bf_debug_cold_redos(h.h, int(reset)))
+    if v < 0:
+        raise RuntimeError("bf_debug_cold_redos failed")
+    return v
+
+
 def evaluate_iou(pst, box6, rot9, uv, poses, search6, rcfg: RefineCfg) -> torch.Tensor:
     """BoxFusion.evaluate_iou (box_fusion.py:413-461) -> fitness[P] float32 on the device."""
     dev = _pick_device(pst, uv)

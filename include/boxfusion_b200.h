@@ -188,6 +188,11 @@ int bf_set_option(bf_handle* h, int key, int value);
  * regime, 1 = mid, 2 = saturated / compact code) + cluster size * 1000 + block size.  No reference counterpart. */
 int bf_refine_last_launch(bf_handle* h);
 
+/* Diagnostic: number of (particle, view) evaluations since the last reset that the latency instantiations of bf_refine /
+ * bf_evaluate_iou redid with plain IEEE divisions because a division operand left the exponent window of their branch-free
+ * ones (zero on real data; tests construct such operands).  Synchronises the device; -1 on error.  No reference counterpart. */
+long long bf_debug_cold_redos(bf_handle* h, int reset);
+
 /* BoxFusion.evaluate_iou (box_fusion.py:413-461): one fitness vector for one box (test/diagnostic entry). */
 int bf_evaluate_iou(bf_handle* h, const float* pst /*[P,6]*/, int P, const float* box6 /*[6]*/, const float* rot9,
                     const float* uv /*[V,16]*/, const float* poses /*[V,16]*/, int V, const float* search6,

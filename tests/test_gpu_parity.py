@@ -516,3 +516,46 @@ def test_sequence_matches_port_longer(monkeypatch):
         for key in sa:
             assert sa[key].shape == sb[key].shape and np.array_equal(_bits(sa[key]), _bits(sb[key])), (k, key)
     assert len(b.box_manager.already_fusion) > 20
+
+
+def test_evaluate_iou_division_operands_outside_the_fast_window():
+    """The latency instantiations divide with the compiler's own fast path minus its per-division range branch (bf_fdiv);
+    an operand outside the exponent window - here the camera-frame x of four corners of every particle is 1e-30, a tiny
+    non-zero numerator - sends the evaluation to the out-of-line redo with plain divisions.  Same bits as the oracle, and the
+    redo is seen to have run; on ordinary inputs it never does."""
+    P, V = 256, 3
+    pst = make_pst(P, seed=3)
+    cfg = make_cfg("ca1m", pst_path=pst, pst_size=P)
+    prob = refine_problem(1, V, seed=2)
+    W, H = prob["size"]
+    K16 = ro.K16_from_K3(prob["K"])
+    bf = api.BoxFusion(cfg)
+    bf.update_intrinsics((W, H), prob["K"])
+    box6 = np.array([0.5, 0.1, 0.2, 1.0, 0.6, 0.8], np.float32)          # x - l/2 == 0 exactly
+    R = np.eye(3, dtype=np.float32)
+    poses = np.tile(np.eye(4, dtype=np.float32), (V, 1, 1))
+    for v in range(V):
+        poses[v, :3, 3] = (-1e-30, 0.05 * v, -3.0)                         # camera 3 m in front; its x is 1e-30 off the box face
+    obs = port.Instances3D((H, W))                                          # observations: a nearby box seen from the same cameras
+    obs.pred_boxes_3d = port.GeneralInstance3DBoxes(torch.from_numpy(np.tile(box6 * np.float32(1.05), (V, 1))), torch.from_numpy(np.tile(R, (V, 1, 1))))
+    obs.cam_pose = torch.from_numpy(poses)
+    obs.project_3d_boxes(prob["K"], H=H, W=W)
+    proj = obs.projected_boxes.numpy()
+    search = np.array([0.0, 0.1, 0.1, 0.0, 0.5, 0.5], np.float32)          # x and l stay put: every particle has the tiny numerator
+    ops.cold_redos()
+    got = bf.evaluate_iou(box6.astype(np.float64), proj, R, np.ones(V, np.float32), poses, search, V)
+    redone = ops.cold_redos()
+    want = ro.evaluate(box6, proj, pst, R, poses, K16, search, H, W, P)
+    assert np.array_equal(_bits(got), _bits(want))
+    assert redone == P * V, redone
+    assert 0.05 < float(np.mean(want)) < 0.95                               # a real overlap, not the degenerate 0 / 1
+    # ordinary geometry: not a single redo
+    prob2 = refine_problem(2, 4, seed=5)
+    ins = port.Instances3D((H, W))
+    ins.pred_boxes_3d = port.GeneralInstance3DBoxes(torch.from_numpy(prob2["tensor"][0]), torch.from_numpy(prob2["R"][0]))
+    ins.cam_pose = torch.from_numpy(prob2["poses"][0])
+    ins.project_3d_boxes(prob2["K"], H=H, W=W)
+    s2 = np.array([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], np.float32)
+    got2 = bf.evaluate_iou(prob2["tensor"][0, 0].astype(np.float64), ins.projected_boxes.numpy(), prob2["R"][0, 0], prob2["scores"][0], prob2["poses"][0], s2, 4)
+    want2 = ro.evaluate(prob2["tensor"][0, 0], ins.projected_boxes.numpy(), pst, prob2["R"][0, 0], prob2["poses"][0], K16, s2, H, W, P)
+    assert np.array_equal(_bits(got2), _bits(want2)) and ops.cold_redos() == 0

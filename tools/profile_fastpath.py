@@ -50,7 +50,7 @@ def main():
     torch.cuda.synchronize()
     pr.disable()
     print(f"API: {1e3 * (time.perf_counter() - t0) / 200:.4f} ms/keyframe wall (under cProfile)")
-    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+    pstats.Stats(pr).sort_stats("tottime" if "--tottime" in sys.argv else "cumulative").print_stats(45)
 
 
 if __name__ == "__main__":

@@ -12,3 +12,9 @@ for l in sys.stdin:
     d = json.loads(l)
     if 'case' in d: print(d['case'], d.get('launch'), d['ms'], d.get('iters_mean'))
 "
+python tools/refine_phase_timing.py 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l)
+    print(d['case'], {k: round(v) for k, v in d['cycles_mean'].items() if v})
+"
