@@ -193,6 +193,14 @@ int bf_refine_last_launch(bf_handle* h);
  * ones (zero on real data; tests construct such operands).  Synchronises the device; -1 on error.  No reference counterpart. */
 long long bf_debug_cold_redos(bf_handle* h, int reset);
 
+/* Diagnostic (tools/eval_profile.py, csrc/bf_debug.cu): runs bf_refine's one-evaluation-per-thread loop for ONE box and ONE
+ * optimiser state with clock64() ticks compiled into the evaluation and returns, per warp, the cycles spent in each of its
+ * sections.  state21 = box6[6], search[6], rot[9]; cycles = [64][16] int64; grid * threads / 32 <= 64; roll != 0 selects the
+ * compact instantiation.  All pointers are device pointers.  No reference counterpart. */
+int bf_debug_eval_profile(const float* pst, int P, int PB, const float* state21, const float* poses, const float* uv, int V,
+                          const float* intr6, int grid, int threads, int roll, int reps, float* out, long long* cycles,
+                          void* stream);
+
 /* BoxFusion.evaluate_iou (box_fusion.py:413-461): one fitness vector for one box (test/diagnostic entry). */
 int bf_evaluate_iou(bf_handle* h, const float* pst /*[P,6]*/, int P, const float* box6 /*[6]*/, const float* rot9,
                     const float* uv /*[V,16]*/, const float* poses /*[V,16]*/, int V, const float* search6,
