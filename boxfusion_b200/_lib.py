@@ -121,6 +121,7 @@ PROTOTYPES = {
     "bf_set_option": (_i32, [_vp, _i32, _i32]),
     "bf_refine_last_launch": (_i32, [_vp]),
     "bf_debug_cold_redos": (ctypes.c_longlong, [_vp, _i32]),
+    "bf_debug_eval_profile": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "bf_evaluate_iou": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(RefineCfg), _vp, _vp]),
 }
 

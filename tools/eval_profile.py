@@ -1,6 +1,5 @@
 """Diagnostic: cycles per section of one (particle, view) evaluation (bf_debug.cu, BF_EVAL_PROFILE ticks in bf_refine_eval.cuh).
 Prints, per case and instantiation, the mean cycles a warp spends in each section of an evaluation."""
-import ctypes
 import json
 import os
 import sys
@@ -38,9 +37,6 @@ def run(name, V, P, C, T, roll, search, dist=2.5, reps=8, seed=11):
     cyc = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
     h = ops.handle(torch.device(dev))
     fn = h.lib.bf_debug_eval_profile
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     grid = min(C, 64 // (T // 32))
     for _ in range(2):
         rc = fn(ptr(pst), P, PB, ptr(state), ptr(po), ptr(uv), V, ptr(intr), grid, T, int(roll), reps, ptr(out), ptr(cyc), h.stream())
