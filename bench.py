@@ -26,6 +26,8 @@ Multi-GPU: independent sequences, one per rank (weak scaling), no data-path coll
 collects the per-rank maps.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -856,4 +858,16 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # exactly ONE line on stdout - the JSON: anything a library prints there meanwhile (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) goes to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    with contextlib.redirect_stdout(_buf):
+        main()
+    sys.stdout.flush()
+    os.dup2(_real_stdout, 1)
+    os.close(_real_stdout)
+    sys.stdout.write(_buf.getvalue())
+    sys.stdout.flush()

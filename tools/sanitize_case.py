@@ -27,5 +27,16 @@ assert all(np.array_equal(a[k], b[k]) for k in ("tensor", "fusion_flat", "alread
 ca, cb = ops.box_corners(dt, dR), ops.box_corners(mt, mR)
 for mode in (ops.IOU_SAMPLED_REF, ops.IOU_ANALYTIC):
     ops.iou3d_matrix(ca, cb, mode=mode, want_counts=True, want_stats=True)
+# the out-of-line redo of the branch-free divisions (bf_eval_view_cold): camera-frame x of four corners is 1e-30
+bf = api.BoxFusion(cfg)
+bf.update_intrinsics((384, 512), np.array([[500.0, 0, 192.0], [0, 500.0, 256.0], [0, 0, 1]], np.float32))
+box6 = np.array([0.5, 0.1, 0.2, 1.0, 0.6, 0.8], np.float32)
+poses = np.tile(np.eye(4, dtype=np.float32), (2, 1, 1))
+poses[:, :3, 3] = (-1e-30, 0.0, -3.0)
+uv = np.tile(np.array([[192, 224], [352, 224], [352, 320], [192, 320], [192, 231], [315, 231], [315, 305], [192, 305]], np.float32), (2, 1, 1))
+ops.cold_redos()
+bf.evaluate_iou(box6.astype(np.float64), uv, np.eye(3, dtype=np.float32), np.ones(2, np.float32), poses,
+                np.array([0.0, 0.1, 0.1, 0.0, 0.5, 0.5], np.float32), 2)
+assert ops.cold_redos() == 2 * 256
 torch.cuda.synchronize()
 print("sanitize case ok: map", eng.N, "fused", len(sess.box_manager.already_fusion))
