@@ -42,6 +42,7 @@ struct bf_engine {
     uint32_t* snapshot;               // [ncap * SNAP_ROW + 2 * ncap + 64] words, allocated on first use
     int32_t* hflags[2];               // pinned host: keep[ncap], success[ncap], state[32]
     cudaEvent_t flag_evt[2];
+    cudaGraphExec_t ra_exec[2];       // [0] NMS phase + flags to slot 0, [1] snapshot + correspondence phase + flags to slot 1
     char err[512];
 };
 
@@ -700,6 +701,7 @@ extern "C" void bf_engine_destroy(bf_engine* e) {
     if (e->h) cudaSetDevice(e->h->device);
     cudaDeviceSynchronize();
     for (int p = 0; p < PH_COUNT + 2; ++p) if (e->exec[p]) cudaGraphExecDestroy(e->exec[p]);
+    for (int i = 0; i < 2; ++i) if (e->ra_exec[i]) cudaGraphExecDestroy(e->ra_exec[i]);
     if (e->snapshot) cudaFree(e->snapshot);
     for (int i = 0; i < 2; ++i) { if (e->hflags[i]) cudaFreeHost(e->hflags[i]); if (e->flag_evt[i]) cudaEventDestroy(e->flag_evt[i]); }
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
@@ -887,38 +889,83 @@ __global__ void bf_engine_snapshot_kernel(bf_engine_ctx c, uint32_t* __restrict_
     }
 }
 
-static int e_flags_async(bf_engine* e, int slot, int rows, int with_success, cudaStream_t st) {
+// the keep / success flags of the rows in play and the state block, written straight into pinned host memory (device-
+// accessible under unified addressing): one kernel instead of three copies, and it can sit inside a captured graph
+__global__ void bf_engine_publish_kernel(bf_engine_ctx c, int32_t* __restrict__ hkeep, int32_t* __restrict__ hsucc,
+                                         uint32_t* __restrict__ hstate) {
+    const int N = c.st->Nall;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+        hkeep[k] = c.keep[k];
+        if (hsucc) hsucc[k] = c.success[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) hstate[threadIdx.x] = ((const uint32_t*)c.st)[threadIdx.x];
+}
+
+static int e_publish(bf_engine* e, int slot, int with_success, cudaStream_t st) {
     int32_t* hp = e->hflags[slot];
     const size_t ncap = (size_t)e->cfg.map_capacity;
-    if (rows) E_CUDA(e, cudaMemcpyAsync(hp, e->keep, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
-    if (rows && with_success) E_CUDA(e, cudaMemcpyAsync(hp + ncap, e->success, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
-    E_CUDA(e, cudaMemcpyAsync(hp + 2 * ncap, e->state, sizeof(bf_engine_state), cudaMemcpyDeviceToHost, st));
-    E_CUDA(e, cudaEventRecord(e->flag_evt[slot], st));
+    const int grid = e->cfg.map_capacity < 4096 ? (e->cfg.map_capacity + 255) / 256 : 16;
+    bf_engine_publish_kernel<<<grid, 256, 0, st>>>(e_ctx(e), hp, with_success ? hp + ncap : nullptr, (uint32_t*)(hp + 2 * ncap));
+    E_LAUNCH_CHECK(e, "bf_engine_publish_kernel");
+    return BF_OK;
+}
+
+static int e_snapshot(bf_engine* e, cudaStream_t st) {
+    const int sgrid = e->cfg.map_capacity < 1024 ? e->cfg.map_capacity : 1024;
+    bf_engine_snapshot_kernel<<<sgrid, 64, 0, st>>>(e_ctx(e), e->snapshot, 0);
+    E_LAUNCH_CHECK(e, "bf_engine_snapshot_kernel");
+    return BF_OK;
+}
+
+// part 0: NMS phase, flags -> slot 0.  part 1: snapshot of what the later phases overwrite, correspondence phase, flags -> slot 1.
+static int e_ra_issue(bf_engine* e, int part, cudaStream_t st) {
+    int rc;
+    if (part == 0) {
+        if ((rc = e_issue(e, 1 << PH_NMS, st, nullptr))) return rc;
+        return e_publish(e, 0, 1, st);
+    }
+    if ((rc = e_snapshot(e, st))) return rc;
+    if ((rc = e_issue(e, 1 << PH_CORR, st, nullptr))) return rc;
+    return e_publish(e, 1, 0, st);
+}
+
+static int e_ra_capture(bf_engine* e, int part) {
+    cudaGraph_t graph = nullptr;
+    E_CUDA(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = e_ra_issue(e, part, e->cap_stream);
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return e_fail(e, BF_ERR_CUDA, "cudaStreamEndCapture", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&e->ra_exec[part], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return e_fail(e, BF_ERR_CUDA, "cudaGraphInstantiate", cudaGetErrorString(ie));
     return BF_OK;
 }
 
 static int e_tail_mask(const bf_engine* e) { return e_full_mask(e) & ~((1 << PH_INGEST) | (1 << PH_NMS) | (1 << PH_CORR)); }
 
+// Five host calls per keyframe: graph (NMS + flags), event, graph (snapshot + correspondence + flags), event, graph (the rest).
 extern "C" int bf_engine_run_ahead(bf_engine* e, int rows, void* stream) {
     if (!e || rows < 0 || rows > e->cfg.map_capacity) return e_fail(e, BF_ERR_INVALID_ARG, "bf_engine_run_ahead", "bad argument");
     bf_device_guard guard(e->h);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ncap = (size_t)e->cfg.map_capacity;
+    int rc;
     if (!e->snapshot) {
         E_CUDA(e, cudaMalloc((void**)&e->snapshot, sizeof(uint32_t) * (ncap * BF_SNAP_ROW + 2 * ncap + 64)));
         for (int i = 0; i < 2; ++i) {
             E_CUDA(e, cudaMallocHost((void**)&e->hflags[i], sizeof(int32_t) * (2 * ncap + 32)));
             E_CUDA(e, cudaEventCreateWithFlags(&e->flag_evt[i], cudaEventDisableTiming));
         }
+        if (e->have_graph)
+            for (int part = 0; part < 2; ++part)
+                if ((rc = e_ra_capture(e, part))) return rc;
     }
-    int rc;
-    if ((rc = e_run(e, 1 << PH_NMS, st))) return rc;
-    if ((rc = e_flags_async(e, 0, rows, 1, st))) return rc;
-    const int sgrid = rows < 1 ? 1 : (rows < 1024 ? rows : 1024);
-    bf_engine_snapshot_kernel<<<sgrid, 64, 0, st>>>(e_ctx(e), e->snapshot, 0);
-    E_LAUNCH_CHECK(e, "bf_engine_snapshot_kernel");
-    if ((rc = e_run(e, 1 << PH_CORR, st))) return rc;
-    if ((rc = e_flags_async(e, 1, rows, 0, st))) return rc;
+    for (int part = 0; part < 2; ++part) {
+        if (e->ra_exec[part]) E_CUDA(e, cudaGraphLaunch(e->ra_exec[part], st));
+        else if ((rc = e_ra_issue(e, part, st))) return rc;
+        E_CUDA(e, cudaEventRecord(e->flag_evt[part], st));
+    }
     return e_run(e, e_tail_mask(e), st);
 }
 

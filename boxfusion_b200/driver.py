@@ -124,7 +124,7 @@ class FusionSession:
             cur_keep_idx = [i - num_before_cat for i in mask if i >= num_before_cat]
             cur_success_nms = [i - num_before_cat for i in success_mask if i >= num_before_cat]
             keep_idx = np.asarray(mask)
-            self.last_mask, self.last_success = [int(m) for m in mask], [int(m) for m in success_mask]
+            self.last_mask, self.last_success = mask, success_mask          # index lists as returned (kept for the parity tests)
             if len(cur_keep_idx) > 0:
                 all_pred_box, all_poses, keep_idx = impl.Instances3D.correspondence_association(
                     cfg, bm, cur_keep_idx, cur_success_nms, pred_instances, cur_global,

@@ -203,6 +203,7 @@ class Session:
         self._stp = self.engine._st()   # stream of the keyframe in flight (looked up once per keyframe)
         self.image_size = None
         self._flag_views = {}           # numpy / ctypes views of the engine's pinned flag buffers, per slot
+        self._ra_launches = None        # kernels of one run-ahead (constant per engine)
 
     # ---- helpers ----------------------------------------------------------------------------------------------
     def _phase(self, phases):
@@ -231,8 +232,10 @@ class Session:
         rc = e.lib.bf_engine_run_ahead(e.e, rows, self._stp)
         if rc:
             e._check(rc, "bf_engine_run_ahead")
-        lc = e.launch_counts
-        ops.Profile.launches += lc[1] + 1 + lc[2] + sum(c for i, c in enumerate(lc[:7]) if i >= 3 and (e.full_mask >> i) & 1) - (1 if e.fuses_finish else 0)
+        if self._ra_launches is None:                              # NMS + publish, snapshot + correspondence + publish, the rest
+            lc = e.launch_counts
+            self._ra_launches = lc[1] + 3 + lc[2] + sum(c for i, c in enumerate(lc[:7]) if i >= 3 and (e.full_mask >> i) & 1) - (1 if e.fuses_finish else 0)
+        ops.Profile.launches += self._ra_launches
         e._state_fresh = False
         self.lists_host = False
         self.ahead = True
