@@ -278,6 +278,20 @@ def run_ours(args, rank, world, local_rank):
     barrier(); wall_e2e = time.perf_counter() - t0
     n_timed = len(step_ms_e2e)
     h2d_b, d2h_b = ops.Profile.h2d_bytes, ops.Profile.d2h_bytes
+    # ---- context: the same API free-running (no L2 flush, no per-step events; one synchronise at the end): what a caller's loop
+    #      over the sequence sees once the engine is warm - keyframes 20..299, host inputs, wall clock ----
+    def run_api_free(frames, skip=20):
+        s_ = FusionSession(api, cfg, device=str(dev))
+        t_ = None
+        for k, kf in enumerate(frames):
+            if k == skip:
+                torch.cuda.synchronize()
+                t_ = time.perf_counter()
+            ins, pose_np = make_instances(s_, kf, api, False)
+            s_.step(kf, ins, pose_np)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t_) / max(len(frames) - skip, 1) if t_ is not None else None
+    free_s = run_api_free(seqs[0][0]) if len(seqs[0][0]) > 40 else None
     # ---- context: the same pass with every call on its own (round 1's implementation; the engine-backed path switched off) ----
     from boxfusion_b200 import fastpath
     fastpath.ENABLED = False
@@ -353,6 +367,10 @@ def run_ours(args, rank, world, local_rank):
                        "note": "same keyframes through bf_engine_step (one C call = one H2D copy + one CUDA-graph launch per keyframe; "
                                "host packing of the detections incl. both pose inverses is inside the timed region); final map "
                                "identical to the reference-shaped API's"},
+        "e2e_free_running": (None if free_s is None else {
+            "ms_per_step": round(1e3 * free_s, 4), "value": round(1.0 / free_s, 1), "unit": "keyframes/s", "rank": 0,
+            "note": "context: the same reference-shaped API over keyframes 20..299 of the sequence in a plain loop (host inputs, no L2 flush, "
+                    "no per-step events, one synchronise at the end): GPU work of one keyframe overlaps the host side of the next"}),
         "e2e_call_by_call": {"ms_per_step": round(sum(step_ms_cbc) / len(step_ms_cbc), 4), "h2d_bytes_per_step": int(cbc_h2d / max(n_all, 1)),
                              "d2h_bytes_per_step": int(cbc_d2h / max(n_all, 1)), "rank": 0,
                              "note": "context: the same keyframes with boxfusion_b200.fastpath.ENABLED = False - every reference-shaped call uploads, "
