@@ -37,6 +37,7 @@ from ._lib import KF_HEADER
 
 ENABLED = True                      # module switch (tests compare the two implementations)
 RUN_AHEAD = True                    # queue the rest of the keyframe behind spatial_association (rolled back if the caller strays)
+ENGINE_KWARGS: dict = {}       # extra FusionEngine arguments of new sessions (tests: use_graph=False runs the same launches eagerly)
 
 _MAP_NATIVE = ("scores", "pred_boxes", "pred_proj_xy", "pred_boxes_3d", "cam_pose", "frame_id", "init_id", "valid_num", "projected_boxes")
 _STORE_NATIVE = ("scores", "pred_boxes_3d", "cam_pose", "projected_boxes")
@@ -172,7 +173,7 @@ class Session:
         self.use_fusion, self.check_valid, self.gap = bool(cfg["box_fusion"]["use"]), bool(cfg["box_fusion"].get("check_valid")), int(cfg["data"]["gap"])
         self.map_dev, self.store_dev = {}, {}        # device of every engine-held field in the caller's own containers
         self.engine = FusionEngine(cfg, device=device, map_capacity=map_capacity, store_capacity=store_capacity,
-                                   fused_capacity=fused_capacity, max_det=max_det, iou_mode=inst_mod.IOU_MODE)
+                                   fused_capacity=fused_capacity, max_det=max_det, iou_mode=inst_mod.IOU_MODE, **ENGINE_KWARGS)
         self.iou_mode = inst_mod.IOU_MODE
         self.dev = self.engine.dev
         self.bm = weakref.ref(bm)

@@ -211,3 +211,12 @@ def test_run_ahead_is_invisible():
                     assert np.array_equal(_bits(sa[key]), _bits(np.asarray(sb[key]))), (k, key)
         _same(a.snapshot(), b.snapshot(), k)
     assert looked >= 4 and a.box_manager._session is not None
+
+
+def test_fast_path_without_graphs(monkeypatch):
+    """The engine behind the API with use_graph=False: every phase and the run-ahead (NMS + flag publication, snapshot +
+    correspondence + flag publication, the rest) issued as plain launches instead of captured graphs - same state."""
+    monkeypatch.setattr(fastpath, "ENGINE_KWARGS", {"use_graph": False})
+    cfg = make_cfg("ca1m", pst_path=make_pst(256, seed=6), pst_size=256)
+    a, _, fast = _pair(dict(n_objects=60, seed=21, max_det=24, shape="ca1m", tilt_noise=0.01), cfg, 14)
+    assert fast >= 9 and a.box_manager._session is not None
