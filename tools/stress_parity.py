@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--seeds", type=int, default=12)
     ap.add_argument("--frames", type=int, default=30)
     ap.add_argument("--with-port", type=int, default=4, help="first K seeds are also checked against the CPU port")
+    ap.add_argument("--seed-base", type=int, default=300, help="scene seed of the first run (another base = another set of sequences)")
     args = ap.parse_args()
     port.IOU_BACKEND = "c_batch"
     stats = {"keyframes": 0, "keyframes_on_engine_backed_api": 0, "swaps_or_merges": 0, "fused": 0, "mismatch": 0}
@@ -35,7 +36,7 @@ def main():
         shape = "scannet" if seed % 2 else "ca1m"
         tilt = (0.0, 0.01, 0.03)[seed % 3]
         n_obj = (40, 90, 160)[seed % 3]
-        scene = SyntheticScene(n_objects=n_obj, seed=300 + seed, max_det=(20, 35, 50)[seed % 3], shape=shape, tilt_noise=tilt,
+        scene = SyntheticScene(n_objects=n_obj, seed=args.seed_base + seed, max_det=(20, 35, 50)[seed % 3], shape=shape, tilt_noise=tilt,
                                new_frac=(0.1, 0.25)[seed % 2])
         P = (128, 256, 500)[seed % 3]
         cfg = make_cfg(shape, pst_path=make_pst(512, seed=seed), pst_size=P)
