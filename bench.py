@@ -377,6 +377,7 @@ def run_ours(args, rank, world, local_rank):
                                      "launches and downloads on its own (round 1's implementation of the API)"},
         "gpu_launches": int(launches), "calls": call_counts, "l2": "flushed between steps (256 MiB memset outside the step events)",
         "final_map_boxes": len(sess.all_pred_box), "keyframes_run": n_all,
+        "refine_division_redos": ops.cold_redos(dev, reset=False),      # evaluations redone with plain divisions (bf_fdiv window): expected 0
         "wall_s": {"resident": round(wall_resident, 3), "e2e": round(wall_e2e, 3), "engine": round(wall_eng, 3)},
         "p50_ms": round(float(np.percentile(step_ms, 50)), 4), "p99_ms": round(float(np.percentile(step_ms, 99)), 4),
         "roofline": roof, "clocks": clocks,
